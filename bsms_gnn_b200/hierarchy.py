@@ -1,0 +1,114 @@
+"""Bi-stride multi-level graph builder (vectorised numpy/scipy; once per mesh, off the hot path).
+
+Produces the same `(m_gs, m_ids)` the reference builds in pure Python with
+`BistrideMultiLayerGraph(flat_edge, num_layers, num_nodes, pos).get_multi_layer_graphs()`
+(reference: src/graph_wrappers/bsms_graph_wrapper.py:30-154, src/graph_wrappers/graph_wrapper.py:67-134):
+
+  per level: connected clusters -> per cluster the seed is the node nearest the cluster centroid
+  (:107-126) -> BFS distance parity from the seed -> keep the smaller of the even/odd sets, even on
+  ties or when there is no odd node (:80-95) -> new adjacency = pattern of (A+I)^2 without the
+  diagonal, restricted to kept nodes and re-indexed (:99-102, :129-154).
+
+Differences from the reference, none of which change the graph: (i) edges of levels >= 1 are emitted
+row-major with SORTED columns (the reference inherits whatever column order the MKL/scipy SpGEMM
+leaves inside a row); (ii) clusters are weakly-connected components, which equals the reference's
+"reachable from the first unvisited node" for the symmetric graphs every mesh produces;
+(iii) only the kept rows/columns of (A+I)^2 are formed.  tests/test_hierarchy.py checks node ids
+exactly and edge sets exactly against golden outputs of the reference builder.
+
+The reference needs 96 s / 5.5 GB for a 2 M-node mesh; this one is what
+bench.py uses to build the large synthetic hierarchies on the GPU box, where /root/reference does
+not exist.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+from scipy.sparse.csgraph import connected_components
+
+
+def _csr_pattern(flat_edge: np.ndarray, n: int) -> sp.csr_matrix:
+    a = sp.csr_matrix((np.ones(flat_edge.shape[1], dtype=np.float32),
+                       (flat_edge[0], flat_edge[1])), shape=(n, n))
+    a.sum_duplicates()
+    a.data[:] = 1.0
+    return a
+
+
+def _bfs_levels(a: sp.csr_matrix, seeds: np.ndarray) -> np.ndarray:
+    """Multi-source BFS depth over directed edges row->col; -1 = unreachable."""
+    n = a.shape[0]
+    indptr, indices = a.indptr, a.indices
+    dist = np.full(n, -1, dtype=np.int64)
+    dist[seeds] = 0
+    frontier = np.asarray(seeds, dtype=np.int64)
+    depth = 0
+    while frontier.size:
+        depth += 1
+        starts = indptr[frontier]
+        counts = indptr[frontier + 1] - starts
+        total = int(counts.sum())
+        if total == 0:
+            break
+        # concatenated neighbour lists of the frontier without a Python loop
+        offs = np.repeat(starts - np.concatenate([[0], np.cumsum(counts)[:-1]]), counts)
+        nbr = indices[np.arange(total, dtype=np.int64) + offs]
+        nbr = nbr[dist[nbr] < 0]
+        if nbr.size == 0:
+            break
+        nbr = np.unique(nbr)
+        dist[nbr] = depth
+        frontier = nbr
+    return dist
+
+
+def bistride_level(flat_edge: np.ndarray, pos: np.ndarray, n: int):
+    """One pooling level: returns (kept node ids sorted [n'], new flat edges [2,E'] int64)."""
+    flat_edge = np.asarray(flat_edge, dtype=np.int64).reshape(2, -1)
+    a = _csr_pattern(flat_edge, n)
+    ncomp, labels = connected_components(a, directed=True, connection="weak")
+    # clusters ordered by their smallest node id, members ascending (graph_wrapper.py:107-134)
+    order = np.argsort(labels, kind="stable")
+    bounds = np.concatenate([[0], np.cumsum(np.bincount(labels, minlength=ncomp))])
+    seeds = np.empty(ncomp, dtype=np.int64)
+    for c in range(ncomp):
+        members = order[bounds[c]:bounds[c + 1]]
+        if members.size == 1:
+            seeds[c] = members[0]
+            continue
+        pc = pos[members]
+        center = np.mean(pc, axis=0)
+        d = np.linalg.norm(pc - center[None, :], 2, axis=-1)
+        seeds[c] = members[np.argmin(d)]
+    dist = _bfs_levels(a, seeds)
+    reach = dist >= 0
+    even = reach & (dist % 2 == 0)
+    odd = reach & (dist % 2 == 1)
+    n_even = np.bincount(labels[even], minlength=ncomp)
+    n_odd = np.bincount(labels[odd], minlength=ncomp)
+    keep_even = (n_even <= n_odd) | (n_odd == 0)
+    kept_mask = np.where(keep_even[labels], even, odd)
+    keep = np.nonzero(kept_mask)[0].astype(np.int64)
+    a1 = (a + sp.identity(n, dtype=np.float32, format="csr")).tocsr()
+    a2 = (a1[keep, :] @ a1[:, keep]).tocsr()
+    a2.setdiag(0)
+    a2.eliminate_zeros()
+    a2.sort_indices()
+    coo = a2.tocoo()
+    new_e = np.stack([coo.row.astype(np.int64), coo.col.astype(np.int64)])
+    return keep, new_e
+
+
+def build_hierarchy(flat_edge: np.ndarray, num_layers: int, num_nodes: int, pos: np.ndarray):
+    """-> (m_gs: list[num_layers+1] of int64 [2,E_l], m_ids: list[num_layers] of int64 [n_{l+1}])."""
+    g = np.asarray(flat_edge, dtype=np.int64).reshape(2, -1)
+    pos_l = np.asarray(pos)
+    n = int(num_nodes)
+    m_gs, m_ids = [g], []
+    for _ in range(num_layers):
+        keep, g = bistride_level(g, pos_l, n)
+        pos_l = pos_l[keep]
+        n = int(keep.shape[0])
+        m_gs.append(g)
+        m_ids.append(keep)
+    return m_gs, m_ids
