@@ -1,0 +1,419 @@
+// GMP block (src/ops/basic.py:26-98): forward and recompute-backward orchestration plus the
+// non-GEMM kernels (edge gather/fiber/combine, LayerNorm + CSR segment sum, LayerNorm backward,
+// segment sums of edge gradients).  BSMS_MODE_FP32 runs the dense layers on the fp32 FFMA GEMMs in
+// gemm_fp32.cuh; the tensor-core modes replace the MLP chains with the fused tcgen05 kernels in
+// umma_chain.cu.
+//
+// Algebra used everywhere: the first edge Linear splits by column block,
+//   W1 [fiber, x_i, x_j] = W1f fiber + W1s x_i + W1d x_j,
+// so the two latent blocks are projected ONCE PER NODE (Ps = x W1s^T, Pd = x W1d^T) and the
+// per-edge work of layer 0 is a gather-add of two projected rows plus a (P+1)-term fiber FMA.
+// That removes 2*128*128*2 of the 164 608 FLOP/edge and turns the layer-0 weight gradient into
+// a node-level GEMM.
+#include "common.cuh"
+#include "gemm_fp32.cuh"
+
+namespace bsms {
+
+constexpr int D = BSMS_LATENT;
+constexpr float LN_EPS = 1e-5f;
+
+// ------------------------------------------------------------------------------------------
+// a0[e] = relu(Ps[src_e] + Pd[dst_e] + b1 + W1f fiber_e), rows in dst-sorted edge order.
+// One warp per edge row, lane owns 4 channels.  PsPd: [B*N, 256] (Ps | Pd).
+// ------------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(256)
+k_edge_combine(const float* __restrict__ PsPd, const float* __restrict__ pos, int pos_batched,
+               const int32_t* __restrict__ src_d, const int32_t* __restrict__ dst_d, const float* __restrict__ W1,
+               const float* __restrict__ b1, float* __restrict__ A0, int B, int N, int E) {
+  const int lane = threadIdx.x & 31;
+  long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= (long long)B * E) return;
+  int b = (int)(row / E), e = (int)(row - (long long)b * E);
+  int i = src_d[e], j = dst_d[e];
+  const float* pb = pos + (pos_batched ? (size_t)b * N * P : 0);
+  float fib[P + 1];
+  float nrm = 0.f;
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    fib[p] = pb[(size_t)i * P + p] - pb[(size_t)j * P + p];
+    nrm += fib[p] * fib[p];
+  }
+  fib[P] = sqrtf(nrm);
+  const int ldw = 2 * D + P + 1;
+  float4 ps = ld4(PsPd + ((size_t)b * N + i) * 256 + lane * 4);
+  float4 pd = ld4(PsPd + ((size_t)b * N + j) * 256 + 128 + lane * 4);
+  float4 bb = ld4(b1 + lane * 4);
+  float v[4] = {ps.x + pd.x + bb.x, ps.y + pd.y + bb.y, ps.z + pd.z + bb.z, ps.w + pd.w + bb.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float* wrow = W1 + (size_t)(lane * 4 + q) * ldw;
+#pragma unroll
+    for (int p = 0; p <= P; ++p) v[q] += wrow[p] * fib[p];
+    v[q] = fmaxf(v[q], 0.f);
+  }
+  st4(A0 + row * D + lane * 4, make_float4(v[0], v[1], v[2], v[3]));
+}
+
+__device__ __forceinline__ void ln_stats(const float4& y, float& mean, float& rstd) {
+  float s = warp_sum(y.x + y.y + y.z + y.w);
+  mean = s * (1.f / D);
+  float dx = y.x - mean, dy = y.y - mean, dz = y.z - mean, dw = y.w - mean;
+  float v = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.f / D);
+  rstd = 1.f / sqrtf(v + LN_EPS);
+}
+
+// aggr[b,n,:] = sum_{k in row_d(n)} LN(Y[b*E + k, :])     (basic.py:18,94) — warp per node
+__global__ void __launch_bounds__(256)
+k_ln_segsum(const float* __restrict__ Y, const int32_t* __restrict__ rowptr_d, float* __restrict__ aggr, int B, int N,
+            int E) {
+  const int lane = threadIdx.x & 31;
+  long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (gw >= (long long)B * N) return;
+  int b = (int)(gw / N), n = (int)(gw - (long long)b * N);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* yb = Y + (size_t)b * E * D + lane * 4;
+  for (int k = rowptr_d[n]; k < rowptr_d[n + 1]; ++k) {
+    float4 y = ld4(yb + (size_t)k * D);
+    float mean, rstd;
+    ln_stats(y, mean, rstd);
+    acc.x += (y.x - mean) * rstd; acc.y += (y.y - mean) * rstd;
+    acc.z += (y.z - mean) * rstd; acc.w += (y.w - mean) * rstd;
+  }
+  st4(aggr + gw * D + lane * 4, acc);
+}
+
+// out = LN(Yn) + x (+ skip)      (basic.py:98, BSMS.py:102) — warp per node row
+__global__ void __launch_bounds__(256)
+k_ln_residual(const float* __restrict__ Yn, const float* __restrict__ x, const float* __restrict__ skip,
+              float* __restrict__ out, long long rows) {
+  const int lane = threadIdx.x & 31;
+  long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows) return;
+  float4 y = ld4(Yn + r * D + lane * 4);
+  float mean, rstd;
+  ln_stats(y, mean, rstd);
+  float4 xv = ld4(x + r * D + lane * 4);
+  float4 o = make_float4((y.x - mean) * rstd + xv.x, (y.y - mean) * rstd + xv.y, (y.z - mean) * rstd + xv.z,
+                         (y.w - mean) * rstd + xv.w);
+  if (skip) {
+    float4 s = ld4(skip + r * D + lane * 4);
+    o.x += s.x; o.y += s.y; o.z += s.z; o.w += s.w;
+  }
+  st4(out + r * D + lane * 4, o);
+}
+
+// LayerNorm backward for rows of Y: gY = rstd * (g - mean(g) - yhat * mean(g * yhat)), where the
+// upstream row is g[b*N + idx[e]] for edge rows (gather of the aggregated gradient) or g[row].
+__global__ void __launch_bounds__(256)
+k_ln_bwd(const float* __restrict__ Y, const float* __restrict__ g, int ldg, const int32_t* __restrict__ idx,
+         int rows_per_b, int g_rows_per_b, float* __restrict__ gY, long long rows) {
+  const int lane = threadIdx.x & 31;
+  long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows) return;
+  long long gr = r;
+  if (idx) {
+    long long b = r / rows_per_b;
+    gr = b * g_rows_per_b + idx[r - b * rows_per_b];
+  }
+  float4 y = ld4(Y + r * D + lane * 4);
+  float mean, rstd;
+  ln_stats(y, mean, rstd);
+  float4 gv = ld4(g + gr * ldg + lane * 4);
+  float4 yh = make_float4((y.x - mean) * rstd, (y.y - mean) * rstd, (y.z - mean) * rstd, (y.w - mean) * rstd);
+  float c1 = warp_sum(gv.x + gv.y + gv.z + gv.w) * (1.f / D);
+  float c2 = warp_sum(gv.x * yh.x + gv.y * yh.y + gv.z * yh.z + gv.w * yh.w) * (1.f / D);
+  st4(gY + r * D + lane * 4, make_float4(rstd * (gv.x - c1 - yh.x * c2), rstd * (gv.y - c1 - yh.y * c2),
+                                         rstd * (gv.z - c1 - yh.z * c2), rstd * (gv.w - c1 - yh.w * c2)));
+}
+
+// gPsPd[b,n,0:128]  = sum_{k in row_s(n)} gU0[b*E + s2d[k]]   (gradient reaching Ps through x_i gathers)
+// gPsPd[b,n,128:256]= sum_{k in row_d(n)} gU0[b*E + k]        (through x_j gathers) — warp per node
+__global__ void __launch_bounds__(256)
+k_edge_grad_segsum(const float* __restrict__ gU0, const int32_t* __restrict__ rowptr_d,
+                   const int32_t* __restrict__ rowptr_s, const int32_t* __restrict__ s2d, float* __restrict__ gPsPd,
+                   int B, int N, int E) {
+  const int lane = threadIdx.x & 31;
+  long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (gw >= (long long)B * N) return;
+  int b = (int)(gw / N), n = (int)(gw - (long long)b * N);
+  const float* gb = gU0 + (size_t)b * E * D + lane * 4;
+  float4 as = make_float4(0.f, 0.f, 0.f, 0.f), ad = as;
+  for (int k = rowptr_s[n]; k < rowptr_s[n + 1]; ++k) {
+    float4 v = ld4(gb + (size_t)s2d[k] * D);
+    as.x += v.x; as.y += v.y; as.z += v.z; as.w += v.w;
+  }
+  for (int k = rowptr_d[n]; k < rowptr_d[n + 1]; ++k) {
+    float4 v = ld4(gb + (size_t)k * D);
+    ad.x += v.x; ad.y += v.y; ad.z += v.z; ad.w += v.w;
+  }
+  st4(gPsPd + gw * 256 + lane * 4, as);
+  st4(gPsPd + gw * 256 + 128 + lane * 4, ad);
+}
+
+// gW1[:, 0:P+1] += gU0^T fiber ; gb1 += colsum(gU0).  Block = 128 threads (one per channel),
+// each block walks a contiguous chunk of edge rows.
+template <int P>
+__global__ void __launch_bounds__(128)
+k_fiber_wgrad(const float* __restrict__ gU0, const float* __restrict__ pos, int pos_batched,
+              const int32_t* __restrict__ src_d, const int32_t* __restrict__ dst_d, float* __restrict__ gW1,
+              float* __restrict__ gb1, int B, int N, int E, int rows_per_block) {
+  const int c = threadIdx.x;
+  long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = min(r0 + rows_per_block, (long long)B * E);
+  float acc[P + 1], accb = 0.f;
+#pragma unroll
+  for (int p = 0; p <= P; ++p) acc[p] = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    int b = (int)(r / E), e = (int)(r - (long long)b * E);
+    int i = src_d[e], j = dst_d[e];
+    const float* pb = pos + (pos_batched ? (size_t)b * N * P : 0);
+    float fib[P + 1], nrm = 0.f;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      fib[p] = pb[(size_t)i * P + p] - pb[(size_t)j * P + p];
+      nrm += fib[p] * fib[p];
+    }
+    fib[P] = sqrtf(nrm);
+    float g = gU0[r * D + c];
+    accb += g;
+#pragma unroll
+    for (int p = 0; p <= P; ++p) acc[p] += g * fib[p];
+  }
+  const int ldw = 2 * D + P + 1;
+#pragma unroll
+  for (int p = 0; p <= P; ++p) atomicAdd(&gW1[(size_t)c * ldw + p], acc[p]);
+  atomicAdd(&gb1[c], accb);
+}
+
+// g_x = g_out + gcat[:, 0:128]   (residual + node-MLP input path); later GEMM accumulates the edge path
+__global__ void k_add_rows(const float* __restrict__ a, const float* __restrict__ b, int ldb, float* __restrict__ out,
+                           long long rows) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * 32) return;
+  long long r = t >> 5;
+  int c = (int)(t & 31) * 4;
+  float4 x = ld4(a + r * D + c), y = ld4(b + r * ldb + c);
+  st4(out + r * D + c, make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w));
+}
+
+struct Sizes {
+  long long Rn, Re;
+};
+
+template <int P>
+static int edge_combine(const float* PsPd, const float* pos, int pos_batched, const bsms_level_plan* pl,
+                        const float* W1, const float* b1, float* A0, int B, cudaStream_t st) {
+  long long rows = (long long)B * pl->n_edges;
+  if (rows == 0) return BSMS_OK;
+  {
+    ProfScope ps_(PK_EDGE_COMBINE, st);
+    k_edge_combine<P><<<ceil_div(rows * 32, 256), 256, 0, st>>>(PsPd, pos, pos_batched, pl->src_d, pl->dst_d, W1, b1, A0,
+                                                                B, pl->n_nodes, pl->n_edges);
+  }
+  BSMS_LAUNCHED();
+  return BSMS_OK;
+}
+
+template <int P>
+static int fiber_wgrad(const float* gU0, const float* pos, int pos_batched, const bsms_level_plan* pl, float* gW1,
+                       float* gb1, int B, cudaStream_t st) {
+  long long rows = (long long)B * pl->n_edges;
+  if (rows == 0) return BSMS_OK;
+  int rpb = (int)std::max<long long>(64, (rows + 148 * 8 - 1) / (148 * 8));
+  {
+    ProfScope ps_(PK_WGRAD, st);
+    k_fiber_wgrad<P><<<ceil_div(rows, rpb), 128, 0, st>>>(gU0, pos, pos_batched, pl->src_d, pl->dst_d, gW1, gb1, B,
+                                                          pl->n_nodes, pl->n_edges, rpb);
+  }
+  BSMS_LAUNCHED();
+  return BSMS_OK;
+}
+
+#define BSMS_TRY(expr)            \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != BSMS_OK) return _rc; \
+  } while (0)
+
+// ---- fp32 forward; when `keep` is set every activation is kept (backward recompute)
+struct Fp32Acts {
+  float *PsPd, *A0, *A1, *A2, *Y, *aggr, *N1, *N2, *N3, *Yn;
+};
+
+static int fp32_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos,
+                        int pos_batched, int B, int P, const Fp32Acts& a, cudaStream_t st) {
+  const int N = pl->n_nodes, E = pl->n_edges;
+  const long long Rn = (long long)B * N, Re = (long long)B * E;
+  const int ldw1 = 2 * D + P + 1;
+  // Ps | Pd = x [W1s ; W1d]^T  : two N=128 GEMMs writing the two halves of PsPd (ld 256)
+  BSMS_TRY(gemm_nt(x, D, nullptr, 0, D, 0, w->w_edge[0] + (P + 1), ldw1, nullptr, nullptr, 0, a.PsPd, 256, Rn, D, 0, st, PK_NODE_FWD_GEMM));
+  BSMS_TRY(gemm_nt(x, D, nullptr, 0, D, 0, w->w_edge[0] + (P + 1 + D), ldw1, nullptr, nullptr, 0, a.PsPd + 128, 256, Rn,
+                   D, 0, st, PK_NODE_FWD_GEMM));
+  if (Re > 0) {
+    if (P == 1) BSMS_TRY(edge_combine<1>(a.PsPd, pos, pos_batched, pl, w->w_edge[0], w->b_edge[0], a.A0, B, st));
+    if (P == 2) BSMS_TRY(edge_combine<2>(a.PsPd, pos, pos_batched, pl, w->w_edge[0], w->b_edge[0], a.A0, B, st));
+    if (P == 3) BSMS_TRY(edge_combine<3>(a.PsPd, pos, pos_batched, pl, w->w_edge[0], w->b_edge[0], a.A0, B, st));
+    BSMS_TRY(gemm_nt(a.A0, D, nullptr, 0, D, 0, w->w_edge[1], D, w->b_edge[1], nullptr, 0, a.A1, D, Re, D, GEMM_RELU, st, PK_EDGE_FWD_GEMM));
+    BSMS_TRY(gemm_nt(a.A1, D, nullptr, 0, D, 0, w->w_edge[2], D, w->b_edge[2], nullptr, 0, a.A2, D, Re, D, GEMM_RELU, st, PK_EDGE_FWD_GEMM));
+    BSMS_TRY(gemm_nt(a.A2, D, nullptr, 0, D, 0, w->w_edge[3], D, w->b_edge[3], nullptr, 0, a.Y, D, Re, D, 0, st, PK_EDGE_FWD_GEMM));
+  }
+  {
+    ProfScope ps_(PK_LN_SEGSUM, st);
+    k_ln_segsum<<<ceil_div(Rn * 32, 256), 256, 0, st>>>(a.Y, pl->rowptr_d, a.aggr, B, N, E);
+  }
+  BSMS_LAUNCHED();
+  BSMS_TRY(gemm_nt(x, D, a.aggr, D, D, D, w->w_node[0], 2 * D, w->b_node[0], nullptr, 0, a.N1, D, Rn, D, GEMM_RELU, st, PK_NODE_FWD_GEMM));
+  BSMS_TRY(gemm_nt(a.N1, D, nullptr, 0, D, 0, w->w_node[1], D, w->b_node[1], nullptr, 0, a.N2, D, Rn, D, GEMM_RELU, st, PK_NODE_FWD_GEMM));
+  BSMS_TRY(gemm_nt(a.N2, D, nullptr, 0, D, 0, w->w_node[2], D, w->b_node[2], nullptr, 0, a.N3, D, Rn, D, GEMM_RELU, st, PK_NODE_FWD_GEMM));
+  BSMS_TRY(gemm_nt(a.N3, D, nullptr, 0, D, 0, w->w_node[3], D, w->b_node[3], nullptr, 0, a.Yn, D, Rn, D, 0, st, PK_NODE_FWD_GEMM));
+  return BSMS_OK;
+}
+
+static Fp32Acts carve(Arena& ar, long long Rn, long long Re, bool keep) {
+  Fp32Acts a;
+  long long re = Re > 0 ? Re : 1;
+  a.PsPd = ar.take<float>(Rn * 256);
+  a.A0 = ar.take<float>(re * D);
+  if (keep) {
+    a.A1 = ar.take<float>(re * D);
+    a.A2 = ar.take<float>(re * D);
+    a.Y = ar.take<float>(re * D);
+  } else {
+    a.A1 = a.A2 = a.Y = a.A0;  // in place: a CTA owns whole rows (BN = N = 128)
+  }
+  a.aggr = ar.take<float>(Rn * D);
+  a.N1 = ar.take<float>(Rn * D);
+  if (keep) {
+    a.N2 = ar.take<float>(Rn * D);
+    a.N3 = ar.take<float>(Rn * D);
+    a.Yn = ar.take<float>(Rn * D);
+  } else {
+    a.N2 = a.N3 = a.Yn = a.N1;
+  }
+  return a;
+}
+}  // namespace bsms
+
+using namespace bsms;
+
+extern "C" size_t bsms_gmp_workspace_bytes(int32_t B, int32_t N, int32_t E, int32_t mode, int32_t backward) {
+  (void)mode;
+  size_t Rn = (size_t)B * N, Re = (size_t)B * (E > 0 ? E : 1);
+  auto f = [](size_t n) { return align_up(n * sizeof(float), 256); };
+  size_t fwd = f(Rn * 256) + f(Re * D) + 2 * f(Rn * D);
+  if (!backward) return fwd + 4096;
+  size_t bwd = f(Rn * 256) + 4 * f(Re * D) + 5 * f(Rn * D)  // kept activations
+               + 2 * f(Re * D) + 2 * f(Rn * D) + 2 * f(Rn * 256);  // gradient ping-pong, gcat, gPsPd
+  return bwd + 4096;
+}
+
+static int check_common(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos,
+                        int B, int P, int mode) {
+  BSMS_CHECK_ARG(pl && w && x && pos, "bsms_gmp: null argument");
+  BSMS_CHECK_ARG(B >= 1, "bsms_gmp: B must be >= 1");
+  BSMS_CHECK_ARG(P >= 1 && P <= 3, "bsms_gmp: pos_dim %d unsupported (1..3)", P);
+  BSMS_CHECK_ARG(mode == BSMS_MODE_FP32, "bsms_gmp: mode %d not built", mode);
+  for (int l = 0; l < 4; ++l)
+    BSMS_CHECK_ARG(w->w_edge[l] && w->b_edge[l] && w->w_node[l] && w->b_node[l], "bsms_gmp: null weight %d", l);
+  return BSMS_OK;
+}
+
+extern "C" int bsms_gmp_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos,
+                                int32_t pos_batched, const float* skip, float* out, int32_t B, int32_t P, int32_t mode,
+                                void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  BSMS_TRY(check_common(pl, w, x, pos, B, P, mode));
+  BSMS_CHECK_ARG(out && ws, "bsms_gmp_forward: null argument");
+  if (ws_bytes < bsms_gmp_workspace_bytes(B, pl->n_nodes, pl->n_edges, mode, 0)) {
+    set_error("bsms_gmp_forward: workspace too small");
+    return BSMS_EWORKSPACE;
+  }
+  const long long Rn = (long long)B * pl->n_nodes, Re = (long long)B * pl->n_edges;
+  Arena ar(ws, ws_bytes);
+  Fp32Acts a = carve(ar, Rn, Re, false);
+  BSMS_TRY(fp32_forward(pl, w, x, pos, pos_batched, B, P, a, st));
+  {
+    ProfScope ps_(PK_OTHER, st);
+    k_ln_residual<<<ceil_div(Rn * 32, 256), 256, 0, st>>>(a.Yn, x, skip, out, Rn);
+  }
+  BSMS_LAUNCHED();
+  return BSMS_OK;
+}
+
+extern "C" int bsms_gmp_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos,
+                                 int32_t pos_batched, const float* g_out, float* g_x, const bsms_gmp_grads* gr,
+                                 int32_t B, int32_t P, int32_t mode, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  BSMS_TRY(check_common(pl, w, x, pos, B, P, mode));
+  BSMS_CHECK_ARG(g_out && g_x && gr && ws, "bsms_gmp_backward: null argument");
+  for (int l = 0; l < 4; ++l)
+    BSMS_CHECK_ARG(gr->w_edge[l] && gr->b_edge[l] && gr->w_node[l] && gr->b_node[l], "bsms_gmp_backward: null grad %d", l);
+  if (ws_bytes < bsms_gmp_workspace_bytes(B, pl->n_nodes, pl->n_edges, mode, 1)) {
+    set_error("bsms_gmp_backward: workspace too small");
+    return BSMS_EWORKSPACE;
+  }
+  const int N = pl->n_nodes, E = pl->n_edges;
+  const long long Rn = (long long)B * N, Re = (long long)B * E;
+  const int ldw1 = 2 * D + P + 1;
+  Arena ar(ws, ws_bytes);
+  Fp32Acts a = carve(ar, Rn, Re, true);
+  float* Ge1 = ar.take<float>((Re > 0 ? Re : 1) * D);
+  float* Ge2 = ar.take<float>((Re > 0 ? Re : 1) * D);
+  float* Gn1 = ar.take<float>(Rn * D);
+  float* Gn2 = ar.take<float>(Rn * D);
+  float* gcat = ar.take<float>(Rn * 256);
+  float* gPsPd = ar.take<float>(Rn * 256);
+  // ---- recompute forward, keeping every activation
+  BSMS_TRY(fp32_forward(pl, w, x, pos, pos_batched, B, P, a, st));
+  // ---- node MLP backward
+  {
+    ProfScope ps_(PK_LN_BWD, st);
+    k_ln_bwd<<<ceil_div(Rn * 32, 256), 256, 0, st>>>(a.Yn, g_out, D, nullptr, 0, 0, Gn1, Rn);
+  }
+  BSMS_LAUNCHED();
+  BSMS_TRY(wgrad(Gn1, D, a.N3, D, gr->w_node[3], D, gr->b_node[3], Rn, st));
+  BSMS_TRY(gemm_kn(Gn1, D, D, w->w_node[3], D, a.N3, D, Gn2, D, Rn, D, GEMM_MASK, st));
+  BSMS_TRY(wgrad(Gn2, D, a.N2, D, gr->w_node[2], D, gr->b_node[2], Rn, st));
+  BSMS_TRY(gemm_kn(Gn2, D, D, w->w_node[2], D, a.N2, D, Gn1, D, Rn, D, GEMM_MASK, st));
+  BSMS_TRY(wgrad(Gn1, D, a.N1, D, gr->w_node[1], D, gr->b_node[1], Rn, st));
+  BSMS_TRY(gemm_kn(Gn1, D, D, w->w_node[1], D, a.N1, D, Gn2, D, Rn, D, GEMM_MASK, st));
+  // layer 0 of the node MLP: input [x | aggr]
+  BSMS_TRY(wgrad(Gn2, D, x, D, gr->w_node[0], 2 * D, gr->b_node[0], Rn, st));
+  BSMS_TRY(wgrad(Gn2, D, a.aggr, D, gr->w_node[0] + D, 2 * D, nullptr, Rn, st));
+  BSMS_TRY(gemm_kn(Gn2, D, D, w->w_node[0], 2 * D, nullptr, 0, gcat, 256, Rn, 256, 0, st));
+  {
+    ProfScope ps_(PK_OTHER, st);
+    k_add_rows<<<ceil_div(Rn * 32, 256), 256, 0, st>>>(g_out, gcat, 256, g_x, Rn);
+  }
+  BSMS_LAUNCHED();
+  // ---- edge MLP backward (upstream of edge row e is g_aggr[dst_e] = gcat[:, 128:])
+  if (Re > 0) {
+    {
+      ProfScope ps_(PK_LN_BWD, st);
+      k_ln_bwd<<<ceil_div(Re * 32, 256), 256, 0, st>>>(a.Y, gcat + 128, 256, pl->dst_d, E, N, Ge1, Re);
+    }
+    BSMS_LAUNCHED();
+    BSMS_TRY(wgrad(Ge1, D, a.A2, D, gr->w_edge[3], D, gr->b_edge[3], Re, st));
+    BSMS_TRY(gemm_kn(Ge1, D, D, w->w_edge[3], D, a.A2, D, Ge2, D, Re, D, GEMM_MASK, st));
+    BSMS_TRY(wgrad(Ge2, D, a.A1, D, gr->w_edge[2], D, gr->b_edge[2], Re, st));
+    BSMS_TRY(gemm_kn(Ge2, D, D, w->w_edge[2], D, a.A1, D, Ge1, D, Re, D, GEMM_MASK, st));
+    BSMS_TRY(wgrad(Ge1, D, a.A0, D, gr->w_edge[1], D, gr->b_edge[1], Re, st));
+    BSMS_TRY(gemm_kn(Ge1, D, D, w->w_edge[1], D, a.A0, D, Ge2, D, Re, D, GEMM_MASK, st));  // Ge2 = gU0
+    if (P == 1) BSMS_TRY(fiber_wgrad<1>(Ge2, pos, pos_batched, pl, gr->w_edge[0], gr->b_edge[0], B, st));
+    if (P == 2) BSMS_TRY(fiber_wgrad<2>(Ge2, pos, pos_batched, pl, gr->w_edge[0], gr->b_edge[0], B, st));
+    if (P == 3) BSMS_TRY(fiber_wgrad<3>(Ge2, pos, pos_batched, pl, gr->w_edge[0], gr->b_edge[0], B, st));
+    {
+      ProfScope ps_(PK_EDGE_GRAD_SEGSUM, st);
+      k_edge_grad_segsum<<<ceil_div(Rn * 32, 256), 256, 0, st>>>(Ge2, pl->rowptr_d, pl->rowptr_s, pl->s2d, gPsPd, B, N, E);
+    }
+    BSMS_LAUNCHED();
+    // node-level layer-0 gradients: gW1s += gPs^T x, gW1d += gPd^T x, g_x += gPs W1s + gPd W1d
+    BSMS_TRY(wgrad(gPsPd, 256, x, D, gr->w_edge[0] + (P + 1), ldw1, nullptr, Rn, st));
+    BSMS_TRY(wgrad(gPsPd + 128, 256, x, D, gr->w_edge[0] + (P + 1 + D), ldw1, nullptr, Rn, st));
+    BSMS_TRY(gemm_kn(gPsPd, 256, D, w->w_edge[0] + (P + 1), ldw1, nullptr, 0, g_x, D, Rn, D, GEMM_ACCUM, st));
+    BSMS_TRY(gemm_kn(gPsPd + 128, 256, D, w->w_edge[0] + (P + 1 + D), ldw1, nullptr, 0, g_x, D, Rn, D, GEMM_ACCUM, st));
+  }
+  return BSMS_OK;
+}

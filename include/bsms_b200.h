@@ -1,0 +1,172 @@
+/*
+ * bsms_b200.h — C-ABI of libbsms_b200.so, the B200 (sm_100a) implementation of the BSMS-GNN
+ * processor hot path.
+ *
+ * The reference (Eydcao/BSMS-GNN) is pure Python and has no FFI of its own; its "operator
+ * interface" for this path is the set of torch.nn.Modules in src/ops/basic.py and src/ops/BSMS.py.
+ * Every entry point below replaces the arithmetic of one of those (file:line cited per function)
+ * and is bound from Python with ctypes by bsms_gnn_b200/_lib.py (see INTEGRATION.md for the
+ * reference-side stub).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only.  Unless a parameter says "host", every pointer is a DEVICE
+ *     pointer on the current CUDA device; `stream` is a cudaStream_t passed as void*.
+ *   - features are fp32 row-major [B, N, C] (B = 1 for un-batched tensors), C = 128 for latent
+ *     features; edge lists are int64 [2, E] exactly as the reference's m_gs (src/ops/BSMS.py:39-57).
+ *   - every function returns 0 on success, a negative BSMS_E* code on failure; the message is
+ *     available from bsms_last_error() (thread-local).  Nothing falls back to the CPU.
+ *   - all kernels are asynchronous on `stream` and graph-capturable unless stated otherwise.
+ */
+#ifndef BSMS_B200_H
+#define BSMS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSMS_OK 0
+#define BSMS_EINVAL (-1)   /* bad argument (shape, null pointer, unsupported width)            */
+#define BSMS_ECUDA (-2)    /* CUDA runtime error; bsms_last_error() has cudaGetErrorString     */
+#define BSMS_EINDEX (-3)   /* edge / node index out of range (reference: ATen index error)     */
+#define BSMS_EWORKSPACE (-4) /* workspace too small                                            */
+
+#define BSMS_LATENT 128    /* the only latent width built (configs/model/(any).yaml: latent_dim 128) */
+
+/* arithmetic of the MLP contractions */
+#define BSMS_MODE_FP32 0      /* fp32 FFMA, exact fp32 products                                  */
+#define BSMS_MODE_FP16X3 1    /* tcgen05 kind::f16, 2-way fp16 split (3 MMAs), fp32 accumulate   */
+#define BSMS_MODE_BF16 2      /* tcgen05 kind::f16 bf16 operands (1 MMA), fp32 accumulate        */
+
+const char* bsms_last_error(void);
+int bsms_version(void);
+/* Device facts the host uses to size grids / report rooflines. out[0]=SM count, out[1]=L2 bytes,
+ * out[2]=max dynamic smem per block, out[3]=compute capability major*10+minor.  (host pointer) */
+int bsms_device_info(int64_t* out4_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * Level plan: the per-graph index structures every kernel consumes.  Built once per mesh level
+ * from the reference's int64 edge list g = m_gs[l]  (g[0] = sender i, g[1] = receiver j;
+ * src/ops/basic.py:66).  All arrays are int32 device buffers owned by the caller.
+ *   dst-sorted order ("_d", stable): position k holds edge perm_d[k]; rowptr_d is the CSR of
+ *     receivers — GMP aggregation and the down transfer reduce over rows of it.
+ *   src-sorted order ("_s", stable): CSR of senders — the up transfer (aggragating=False) and
+ *     every backward gather reduce over rows of it; s2d[k] is the dst-sorted position of the edge
+ *     at src-sorted position k.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct bsms_level_plan {
+  int32_t n_nodes;
+  int32_t n_edges;
+  const int32_t* src_d;    /* [E] */
+  const int32_t* dst_d;    /* [E] */
+  const int32_t* rowptr_d; /* [N+1] */
+  const int32_t* perm_d;   /* [E] */
+  const int32_t* src_s;    /* [E] */
+  const int32_t* dst_s;    /* [E] */
+  const int32_t* rowptr_s; /* [N+1] */
+  const int32_t* s2d;      /* [E] */
+} bsms_level_plan;
+
+size_t bsms_plan_workspace_bytes(int64_t n_edges, int64_t n_nodes);
+/* Fills the eight arrays of `out` (pre-allocated by the caller with the sizes above) from g.
+ * status_dev: int32[4] device scratch; after the call (which synchronises the stream — plan
+ * building is one-time, off the hot path) an out-of-range index yields BSMS_EINDEX. */
+int bsms_plan_build(const int64_t* g, int64_t n_edges, int64_t n_nodes, const bsms_level_plan* out,
+                    int32_t* status_dev, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * WeightedEdgeConv.cal_ew (src/ops/basic.py:142-167): deg_i = out-degree, s_e = w_i/deg_i,
+ * aggr_w_j = sum_{e: dst=j} s_e + 1e-12, ew_e = s_e / aggr_w_j.   w: [N].
+ * Outputs: ew_orig [E] in the caller's edge order (what the reference returns), ew_d / ew_s the
+ * same weights in the plan's two orders (what the transfer kernels read), aggr_w [N].
+ * Any of ew_orig may be NULL.  The reference raises when max(g[0])+1 != N; the host checks that.
+ * ------------------------------------------------------------------------------------------- */
+int bsms_cal_ew(const bsms_level_plan* plan, const float* w, float* ew_orig, float* ew_d,
+                float* ew_s, float* aggr_w, void* stream);
+/* ew given in the caller's edge order -> the plan's two orders (for WeightedEdgeConv.forward
+ * called with arbitrary user weights, src/ops/basic.py:107). */
+int bsms_permute_ew(const bsms_level_plan* plan, const float* ew_orig, float* ew_d, float* ew_s,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * WeightedEdgeConv.forward (src/ops/basic.py:107-140), x: [B,N,C] -> out: [B,N,C], any C >= 1.
+ *   up == 0 (aggragating=True):  out[j] = sum_{e: dst=j} ew_e x[i_e]    (reads ew_d)
+ *   up == 1 (aggragating=False): out[i] = sum_{e: src=i} ew_e x[j_e]    (reads ew_s)
+ * The two are adjoint, so each is the other's backward.  Atomic-free, deterministic.
+ * ------------------------------------------------------------------------------------------- */
+int bsms_edge_conv(const bsms_level_plan* plan, const float* ew, const float* x, float* out,
+                   int32_t B, int32_t C, int32_t up, void* stream);
+/* Down transfer fused with pooling (src/ops/BSMS.py:74-89): out[b,k,:] = conv_down(x)[b,ids[k],:],
+ * only the kept rows are formed.  ids: int32 [n_keep]. */
+int bsms_conv_down_pool(const bsms_level_plan* plan, const float* ew_d, const int32_t* ids,
+                        int32_t n_keep, const float* x, float* out, int32_t B, int32_t C,
+                        void* stream);
+/* Unpool fused with the up transfer (src/ops/BSMS.py:98-100): out = conv_up(unpool(hc)) without
+ * materialising the zero-filled tensor.  inv: int32 [N], coarse row of a fine node or -1. */
+int bsms_unpool_conv_up(const bsms_level_plan* plan, const float* ew_s, const int32_t* inv,
+                        int32_t n_keep, const float* hc, float* out, int32_t B, int32_t C,
+                        void* stream);
+/* Pooling gather out[b,k,:] = x[b,ids[k],:] (src/ops/BSMS.py:79-89) and Unpool.forward
+ * (src/ops/basic.py:176-201; zero-fill + row injection). */
+int bsms_gather_rows(const float* x, const int32_t* ids, int32_t n_keep, int32_t n_rows, float* out,
+                     int32_t B, int32_t C, void* stream);
+int bsms_unpool_rows(const float* h, const int32_t* ids, int32_t n_keep, int32_t n_rows, float* out,
+                     int32_t B, int32_t C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * GMP block (src/ops/basic.py:26-98), latent 128, hidden_layer 3, pos_dim P in {1,2,3}.
+ * Weights are the reference's own tensors, untouched: w_edge[l] = mlp_edge.seq.{2l}.weight
+ * ([128, 2*128+P+1] for l=0, [128,128] after), b_edge[l] its bias, same for mlp_node
+ * ([128,256] for l=0).  Column order of layer 0: edge [dir(P), norm, x_src(128), x_dst(128)]
+ * (basic.py:85-90), node [x(128), aggr(128)] (basic.py:97).
+ *   out = LN(mlp_node([x, sum_{e->j} LN(mlp_edge([fiber_e, x_i, x_j]))])) + x  (+ skip if given)
+ * x: [B,N,128]; pos: [N,P] (pos_batched=0) or [B,N,P]; out: [B,N,128].
+ * ------------------------------------------------------------------------------------------- */
+typedef struct bsms_gmp_weights {
+  const float* w_edge[4];
+  const float* b_edge[4];
+  const float* w_node[4];
+  const float* b_node[4];
+} bsms_gmp_weights;
+
+typedef struct bsms_gmp_grads { /* accumulated into (+=); all required in backward */
+  float* w_edge[4];
+  float* b_edge[4];
+  float* w_node[4];
+  float* b_node[4];
+} bsms_gmp_grads;
+
+/* bytes of scratch bsms_gmp_forward / bsms_gmp_backward need for this problem size */
+size_t bsms_gmp_workspace_bytes(int32_t B, int32_t n_nodes, int32_t n_edges, int32_t mode,
+                                int32_t backward);
+int bsms_gmp_forward(const bsms_level_plan* plan, const bsms_gmp_weights* w, const float* x,
+                     const float* pos, int32_t pos_batched, const float* skip /* may be NULL */,
+                     float* out, int32_t B, int32_t P, int32_t mode, void* workspace,
+                     size_t workspace_bytes, void* stream);
+/* Backward of the block above by recomputation (nothing is saved by forward): given g_out
+ * [B,N,128] writes g_x [B,N,128] (gradient w.r.t. x INCLUDING the residual path; the gradient
+ * w.r.t. skip is g_out itself) and accumulates the 16 parameter gradients.  No gradient flows to
+ * pos (it is an input, src/ops/BSMS.py:75 runs under the same autograd but pos never requires
+ * grad in the reference's use). */
+int bsms_gmp_backward(const bsms_level_plan* plan, const bsms_gmp_weights* w, const float* x,
+                      const float* pos, int32_t pos_batched, const float* g_out, float* g_x,
+                      const bsms_gmp_grads* grads, int32_t B, int32_t P, int32_t mode,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline pass).
+ * Kinds: 0 edge-MLP forward GEMM/chain, 1 node-level forward GEMMs, 2 edge gather+combine,
+ * 3 LayerNorm+segment-sum, 4 dgrad, 5 wgrad, 6 LayerNorm backward, 7 edge-gradient segment sums,
+ * 8 transfer (restriction/prolongation/conv), 9 other.  Host pointers; collect synchronises. */
+#define BSMS_PROF_KINDS 10
+int bsms_prof_enable(int on);
+int bsms_prof_collect(double* ms_by_kind_host, int64_t* launches_by_kind_host, int n_kinds);
+
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t bsms_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSMS_B200_H */

@@ -1,0 +1,140 @@
+"""GPU parity of the whole processor (BSGMP forward + backward through the C-ABI):
+  * against golden vectors produced by the unmodified reference (tests/golden/*.npz),
+  * against the CPU oracle on seeded inputs,
+  * at sizes the oracle cannot reach, through size-independent properties (batch consistency,
+    permutation invariance of the edge order, linearity of the transfer operators).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bsms_oracle as O
+from tests.util import bsgmp_inputs, load_hier, load_npz, max_rel
+
+pytestmark = pytest.mark.gpu
+FWD_TOL = 1e-5   # BASELINE.json north_star: forward within 1e-5 relative fp32
+GRAD_TOL = 5e-4  # fp32 backward noise floor of the reference itself (tests/test_oracle.py)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def build(d, P, seed, dev, mode="fp32"):
+    from bsms_gnn_b200.ops import BSGMP
+    m = BSGMP(d, 128, 3, P, mode=mode).to(dev)
+    m.load_state_dict(O.init_params(d, pos_dim=P, seed=seed))
+    return m
+
+
+@pytest.mark.parametrize("case,hname", [
+    ("chain11", "chain11"), ("grid12", "grid12"), ("grid12_b3", "grid12"),
+    ("grid12_b2_sharedpos", "grid12"), ("ico3", "ico3"), ("twoclusters", "twoclusters"),
+    ("grid44", "grid44"), ("grid72", "grid72"), ("grid72d7", "grid72d7")])
+def test_bsgmp_against_reference_golden(dev, case, hname):
+    rec = load_npz(f"bsgmp_{case}.npz")
+    m_gs, m_ids, pos, d = load_hier(hname)
+    h, ps = bsgmp_inputs(rec, pos, pos.shape[0])
+    model = build(d, int(rec["P"]), int(rec["seed"]), dev)
+    grads = "grad_h" in rec.files
+    hg = h.to(dev).requires_grad_(grads)
+    out = model(hg, [i.to(dev) for i in m_ids], [g.to(dev) for g in m_gs], ps.to(dev))
+    assert out.shape == h.shape
+    rs = int(rec["row_stride"])
+    assert max_rel(out.detach().cpu()[..., ::rs, :], rec["out"]) < FWD_TOL
+    assert abs(float(out.detach().double().abs().sum()) / float(rec["out_abs_sum"]) - 1) < 1e-5
+    if grads:
+        out.square().mean().backward()
+        assert max_rel(hg.grad.cpu()[..., ::rs, :], rec["grad_h"]) < GRAD_TOL
+        sd = dict(model.named_parameters())
+        for k in rec.files:
+            if k.startswith("grad:"):
+                assert max_rel(sd[k[5:]].grad.cpu(), rec[k]) < GRAD_TOL, k
+        norms = np.array([float(v.grad.double().norm()) for _, v in sorted(sd.items())])
+        assert np.allclose(norms, rec["grad_norms"], rtol=2e-4)
+
+
+def test_bsgmp_fwd_bwd_against_fp64_oracle(dev):
+    m_gs, m_ids, pos, d = load_hier("grid44")
+    gen = torch.Generator().manual_seed(21)
+    h = torch.randn(2, pos.shape[0], 128, generator=gen)
+    ps = pos.unsqueeze(0) + 0.05 * torch.randn(2, pos.shape[0], 2, generator=gen)
+    p64 = {k: v.double().requires_grad_(True) for k, v in O.init_params(d, seed=22).items()}
+    h64 = h.double().requires_grad_(True)
+    ref = O.bsgmp(h64, m_ids, m_gs, ps.double(), p64, d)
+    ref.square().mean().backward()
+    model = build(d, 2, 22, dev)
+    hg = h.to(dev).requires_grad_(True)
+    out = model(hg, [i.to(dev) for i in m_ids], [g.to(dev) for g in m_gs], ps.to(dev))
+    out.square().mean().backward()
+    assert max_rel(out.detach().cpu(), ref.detach()) < FWD_TOL
+    assert max_rel(hg.grad.cpu(), h64.grad) < GRAD_TOL
+    for k, v in model.named_parameters():
+        assert max_rel(v.grad.cpu(), p64[k].grad) < GRAD_TOL, k
+
+
+def test_batch_rows_are_independent_and_edge_order_is_irrelevant(dev):
+    """Properties that hold at any size: a batched call equals per-sample calls, and permuting the
+    caller's edge list (the plan re-sorts it) changes nothing beyond fp32 summation order."""
+    m_gs, m_ids, pos, d = load_hier("grid72")
+    model = build(d, 2, 31, dev)
+    gen = torch.Generator().manual_seed(32)
+    h = torch.randn(3, pos.shape[0], 128, generator=gen).to(dev)
+    gs = [g.to(dev) for g in m_gs]
+    ids = [i.to(dev) for i in m_ids]
+    with torch.no_grad():
+        out = model(h, ids, gs, pos.to(dev))
+        for b in range(3):
+            ob = model(h[b].contiguous(), ids, gs, pos.to(dev))
+            assert max_rel(ob, out[b]) < 2e-6
+        gs_perm = [g[:, torch.randperm(g.shape[1], generator=gen).to(dev)].contiguous() for g in gs]
+        out_p = model(h, ids, gs_perm, pos.to(dev))
+    assert max_rel(out_p, out) < 5e-6
+
+
+def test_large_mesh_properties(dev):
+    """200x200 grid (40 k nodes, 238 k level-0 edges, depth 4) built on the box with the package's
+    own hierarchy builder: transfer operators are linear and adjoint, restriction of a constant is
+    that constant (the weights of every kept node sum to 1, src/ops/basic.py:163-165)."""
+    from bsms_gnn_b200 import hierarchy, meshgen, plan
+    from bsms_gnn_b200.ops import _ProlongFunction, _RestrictFunction
+    posn, cells = meshgen.tri_grid(200, 200)
+    fe = meshgen.cells_to_flat_edge(cells)
+    m_gs, m_ids = hierarchy.build_hierarchy(fe, 4, posn.shape[0], posn)
+    gs = [torch.from_numpy(g).to(dev) for g in m_gs]
+    ids = [torch.from_numpy(i).to(dev) for i in m_ids]
+    hp = plan.hierarchy_plan(gs, ids, posn.shape[0])
+    gen = torch.Generator().manual_seed(5)
+    for l in range(4):
+        x = torch.randn(1, hp.n[l], 128, generator=gen).to(dev)
+        y = torch.randn(1, hp.n[l + 1], 128, generator=gen).to(dev)
+        rx = _RestrictFunction.apply(x, hp, l)
+        py = _ProlongFunction.apply(y, hp, l)
+        lhs, rhs = float((rx.double() * y.double()).sum()), float((x.double() * py.double()).sum())
+        assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), 1.0)  # <R x, y> == <x, P y>
+        ones = torch.ones(1, hp.n[l], 128, device=dev)
+        assert float((_RestrictFunction.apply(ones, hp, l) - 1).abs().max()) < 1e-5
+        r2 = _RestrictFunction.apply(2.5 * x + ones, hp, l)
+        assert max_rel(r2, 2.5 * rx + 1) < 1e-5
+    model = build(4, 2, 41, dev)
+    h = torch.randn(hp.n[0], 128, generator=gen).to(dev)
+    with torch.no_grad():
+        out = model(h, ids, gs, torch.from_numpy(posn).to(dev))
+    assert torch.isfinite(out).all() and out.shape == h.shape
+
+
+def test_error_conventions(dev):
+    from bsms_gnn_b200.ops import BSGMP
+    m_gs, m_ids, pos, d = load_hier("grid12")
+    model = build(d, 2, 1, dev)
+    gs = [g.to(dev) for g in m_gs]
+    ids = [i.to(dev) for i in m_ids]
+    with pytest.raises(NotImplementedError):
+        model(torch.zeros(1, 1, 144, 128, device=dev), ids, gs, pos.to(dev))
+    with pytest.raises(IndexError):
+        model(torch.zeros(144, 128, device=dev), ids[:1], gs, pos.to(dev))
+    bad = [gs[0].clone(), gs[1], gs[2]]
+    bad[0][0, 0] = 999
+    with pytest.raises(IndexError):
+        model(torch.zeros(144, 128, device=dev), ids, bad, pos.to(dev))
