@@ -1,0 +1,388 @@
+// Fused GMP edge stage on tcgen05 (sm_100a):  gather Ps[src]+Pd[dst] (+fiber, +b1) -> ReLU ->
+// 3 x (128x128x128 UMMA + bias [+ReLU]) -> LayerNorm -> segmented sum over dst-sorted rows ->
+// red.add into aggr.  No per-edge tensor ever reaches HBM.   (reference: src/ops/basic.py:66-94)
+//
+// CTA = 256 threads = 2 warpgroups; each warpgroup owns one 128-edge tile at a time (thread = edge
+// row = TMEM lane) with a private TMEM region [D 128 cols | A_hi 64 | A_lo 64], so the two tiles
+// ping-pong: one warpgroup's CUDA-core epilogue overlaps the other's MMAs.  Activations never
+// leave TMEM between layers (tcgen05.ld -> bias/ReLU/convert in registers -> tcgen05.st as the
+// next A operand, TS-form MMA); the three weight matrices are staged ONCE per CTA into shared
+// memory by cp.async.bulk (pre-packed in the 128B-swizzled K-major UMMA layout) and stay resident
+// for the whole persistent loop.
+//
+// NSPLIT = 1: bf16 operands (BSMS_MODE_BF16).  NSPLIT = 2: fp16 hi/lo split of both operands, 3 MMAs
+// per K step into one fp32 accumulator (BSMS_MODE_FP16X3): x ~ hi + lo with 22 significant bits, the
+// dropped lo*lo term is 2^-22 relative — the fp32-parity mode.  Operands are pre-scaled by exact
+// powers of two (activations 2^4, weights 2^8) so the lo parts stay in fp16's normal range; the
+// accumulator is rescaled by 2^-12 in the epilogue.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace bsms {
+using namespace umma;
+
+constexpr int kD = BSMS_LATENT;
+constexpr uint32_t kWBlk = 128 * 128 * 2;  // one packed 128x128 16-bit operand block (32 KB)
+constexpr float kActScale = 16.f;          // 2^4
+constexpr float kWScale = 256.f;           // 2^8
+
+// byte offset of element (n, k) inside a packed block = its shared-memory image
+__host__ __device__ inline uint32_t wblk_offset(int n, int k) {
+  return (uint32_t)((k >> 6) * 16384 + n * 128 + ((((k & 63) >> 3) ^ (n & 7)) << 4) + (k & 7) * 2);
+}
+
+struct PackList {
+  const float* w[8];
+  int ld[8];
+  int n;
+};
+
+// fp32 [128 x 128] (row n, ld) -> packed 16-bit block(s).  grid = (n_blocks), block = 256
+template <int NSPLIT>
+__global__ void k_pack_weights(PackList pl, uint8_t* __restrict__ out) {
+  const int blk = blockIdx.x;
+  const float* W = pl.w[blk];
+  const int ld = pl.ld[blk];
+  uint8_t* o = out + (size_t)blk * NSPLIT * kWBlk;
+  for (int idx = threadIdx.x; idx < 128 * 128; idx += blockDim.x) {
+    int n = idx >> 7, k = idx & 127;
+    float v = W[(size_t)n * ld + k];
+    uint32_t off = wblk_offset(n, k);
+    if (NSPLIT == 1) {
+      *reinterpret_cast<__nv_bfloat16*>(o + off) = __float2bfloat16_rn(v);
+    } else {
+      float s = v * kWScale;
+      __half hi = __float2half_rn(s);
+      __half lo = __float2half_rn(s - __half2float(hi));
+      *reinterpret_cast<__half*>(o + off) = hi;
+      *reinterpret_cast<__half*>(o + kWBlk + off) = lo;
+    }
+  }
+}
+
+struct EdgeChainParams {
+  const float* PsPd;  // [B*N, 256]
+  const float* pos;
+  int pos_batched, P;
+  const int32_t* src_d;
+  const int32_t* dst_d;
+  const float* W1;  // mlp_edge layer 0 weight [128, 2*128+P+1] (fiber columns are read from it)
+  const float* b[4];
+  const uint8_t* wpack;  // [3][NSPLIT] packed blocks
+  float* aggr;           // [B*N, 128], zero-initialised
+  int B, N, E;
+  long long rows;
+  int ntiles;
+  float* dbg;
+  int dbg_stage;
+};
+
+template <int NSPLIT>
+__device__ __forceinline__ void store_act32(uint32_t a_tmem, int c0, const float (&v)[32]) {
+  // 32 fp32 values of this thread's row (channels c0..c0+31) -> 16 packed columns of A (hi [, lo])
+  uint32_t hi[16];
+  if (NSPLIT == 1) {
+#pragma unroll
+    for (int t = 0; t < 16; ++t) hi[t] = pack_bf16(v[2 * t], v[2 * t + 1]);
+    tmem_st16(a_tmem + (c0 >> 1), hi);
+  } else {
+    uint32_t lo[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      float s0 = v[2 * t] * kActScale, s1 = v[2 * t + 1] * kActScale;
+      __half h0 = __float2half_rn(s0), h1 = __float2half_rn(s1);
+      __half l0 = __float2half_rn(s0 - __half2float(h0)), l1 = __float2half_rn(s1 - __half2float(h1));
+      hi[t] = pack_f16(h0, h1);
+      lo[t] = pack_f16(l0, l1);
+    }
+    tmem_st16(a_tmem + (c0 >> 1), hi);
+    tmem_st16(a_tmem + 64 + (c0 >> 1), lo);
+  }
+}
+
+template <int NSPLIT, int CH>
+__global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int NW = 3 * NSPLIT;
+  constexpr uint32_t FMT = (NSPLIT == 1) ? 1u : 0u;  // bf16 : f16
+  constexpr uint32_t IDESC = make_idesc(FMT, 128, 128);
+  constexpr float OUT_SCALE = (NSPLIT == 1) ? 1.f : 1.f / (kActScale * kWScale);
+  constexpr int G = 32 / CH;        // row groups per warp in the segmented reduce
+  constexpr int RPG = 32 / G;       // rows per group
+  const uint32_t s0 = smem_u32(smem_raw);
+  const uint32_t sbase = (s0 + 1023u) & ~1023u;
+  uint8_t* sp = smem_raw + (sbase - s0);
+  uint8_t* s_w = sp;
+  float* s_bias = reinterpret_cast<float*>(sp + NW * kWBlk);  // [4][128]
+  float4* s_F = reinterpret_cast<float4*>(s_bias + 512);      // [128]
+  float* s_stage = reinterpret_cast<float*>(s_F + 128);       // [8][32][CH+1]
+  int* s_tgt = reinterpret_cast<int*>(s_stage + 8 * 32 * (CH + 1));
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tgt + 256);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wg = warp >> 2, tw = tid & 127, q = warp & 3;
+  const uint32_t bar_w = smem_u32(&s_bar[0]);
+  const uint32_t bar_m = smem_u32(&s_bar[1 + wg]);
+
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(smem_u32(&s_bar[1]), 1);
+    mbar_init(smem_u32(&s_bar[2]), 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
+  for (int i = tid; i < 512; i += 256) s_bias[i] = p.b[i >> 7][i & 127];
+  {
+    const int ldw1 = 2 * kD + p.P + 1;
+    for (int c = tid; c < 128; c += 256) {
+      float f[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int k = 0; k <= p.P; ++k) f[k] = p.W1[(size_t)c * ldw1 + k];
+      s_F[c] = make_float4(f[0], f[1], f[2], f[3]);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+  if (tid == 0) {
+    mbar_expect_tx(bar_w, NW * kWBlk);
+    for (int blk = 0; blk < NW; ++blk) bulk_g2s(sbase + blk * kWBlk, p.wpack + (size_t)blk * kWBlk, kWBlk, bar_w);
+  }
+  const uint32_t d_tmem = tmem_base + wg * 256;
+  const uint32_t a_tmem = d_tmem + 128;
+  const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+  uint32_t phase = 0;
+  bool weights_ready = false;
+  float* stage = s_stage + warp * 32 * (CH + 1);
+  int* tgt = s_tgt + warp * 32;
+
+  for (int tile = blockIdx.x * 2 + wg; tile < p.ntiles; tile += gridDim.x * 2) {
+    const long long row = (long long)tile * 128 + tw;
+    const bool valid = row < p.rows;
+    int b = 0, i = 0, j = 0;
+    if (valid) {
+      b = (int)(row / p.E);
+      int e = (int)(row - (long long)b * p.E);
+      i = p.src_d[e];
+      j = p.dst_d[e];
+    }
+    tgt[lane] = valid ? b * p.N + j : -1;
+    // ---- prologue: fiber, gather-add, ReLU -> A
+    float fib[4] = {0.f, 0.f, 0.f, 0.f};
+    if (valid) {
+      const float* pb = p.pos + (p.pos_batched ? (size_t)b * p.N * p.P : 0);
+      float nrm = 0.f;
+      for (int k = 0; k < p.P; ++k) {
+        float dlt = pb[(size_t)i * p.P + k] - pb[(size_t)j * p.P + k];
+        fib[k] = dlt;
+        nrm += dlt * dlt;
+      }
+      fib[p.P] = sqrtf(nrm);
+    }
+    const float* ps_row = p.PsPd + ((size_t)b * p.N + i) * 256;
+    const float* pd_row = p.PsPd + ((size_t)b * p.N + j) * 256 + 128;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      float v[32];
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4) {
+        float4 a = valid ? ld4(ps_row + c0 + q4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 d = valid ? ld4(pd_row + c0 + q4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[q4 * 4 + 0] = a.x + d.x; v[q4 * 4 + 1] = a.y + d.y; v[q4 * 4 + 2] = a.z + d.z; v[q4 * 4 + 3] = a.w + d.w;
+      }
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        float4 f = s_F[c0 + t];
+        float x = v[t] + s_bias[c0 + t] + f.x * fib[0] + f.y * fib[1] + f.z * fib[2] + f.w * fib[3];
+        v[t] = valid ? fmaxf(x, 0.f) : 0.f;
+      }
+      if (p.dbg && p.dbg_stage == 0 && valid) {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) p.dbg[row * 128 + c0 + t] = v[t];
+      }
+      store_act32<NSPLIT>(a_tmem + lane_off, c0, v);
+    }
+    // ---- three UMMA layers
+#pragma unroll 1
+    for (int layer = 0; layer < 3; ++layer) {
+      wait_st();
+      fence_before_sync();
+      bar_sync(1 + wg, 128);
+      if (tw == 0) {
+        if (!weights_ready) {
+          mbar_wait(bar_w, 0);
+          weights_ready = true;
+        }
+        fence_after_sync();
+        const uint32_t wb = sbase + layer * NSPLIT * kWBlk;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t koff = (ks >> 2) * 16384 + (ks & 3) * 32;
+          const uint64_t bhi = smem_desc_sw128(wb + koff, 16, 1024);
+          mma_ts(d_tmem, a_tmem + ks * 8, bhi, IDESC, ks > 0);
+          if (NSPLIT == 2) {
+            const uint64_t blo = smem_desc_sw128(wb + kWBlk + koff, 16, 1024);
+            mma_ts(d_tmem, a_tmem + 64 + ks * 8, bhi, IDESC, 1);
+            mma_ts(d_tmem, a_tmem + ks * 8, blo, IDESC, 1);
+          }
+        }
+        mma_commit(bar_m);
+      }
+      mbar_wait(bar_m, phase);
+      phase ^= 1;
+      fence_after_sync();
+      const float* bias = s_bias + (layer + 1) * 128;
+      if (layer < 2) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(d_tmem + lane_off + c0, r);
+          wait_ld();
+          float v[32];
+#pragma unroll
+          for (int t = 0; t < 32; ++t) v[t] = fmaxf(__uint_as_float(r[t]) * OUT_SCALE + bias[c0 + t], 0.f);
+          if (p.dbg && p.dbg_stage == layer + 1 && valid) {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) p.dbg[row * 128 + c0 + t] = v[t];
+          }
+          store_act32<NSPLIT>(a_tmem + lane_off, c0, v);
+        }
+      } else {
+        // ---- final: LayerNorm over the row (two passes over TMEM), then segmented reduce by dst
+        float sum = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(d_tmem + lane_off + c0, r);
+          wait_ld();
+#pragma unroll
+          for (int t = 0; t < 32; ++t) sum += __uint_as_float(r[t]) * OUT_SCALE + bias[c0 + t];
+        }
+        const float mean = sum * (1.f / 128.f);
+        float ssq = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(d_tmem + lane_off + c0, r);
+          wait_ld();
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            float dlt = __uint_as_float(r[t]) * OUT_SCALE + bias[c0 + t] - mean;
+            ssq += dlt * dlt;
+          }
+        }
+        const float rstd = 1.f / sqrtf(ssq * (1.f / 128.f) + 1e-5f);
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(d_tmem + lane_off + c0, r);
+          wait_ld();
+          if (p.dbg && p.dbg_stage == 3 && valid) {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) p.dbg[row * 128 + c0 + t] = __uint_as_float(r[t]) * OUT_SCALE + bias[c0 + t];
+          }
+#pragma unroll
+          for (int sub = 0; sub < 32; sub += CH) {
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < CH; ++t)
+              stage[lane * (CH + 1) + t] = (__uint_as_float(r[sub + t]) * OUT_SCALE + bias[c0 + sub + t] - mean) * rstd;
+            __syncwarp();
+            // lanes switch to channel ownership: ch = lane % CH, row group = lane / CH
+            const int ch = lane % CH, grp = lane / CH;
+            float acc = 0.f;
+            int cur = -1;
+            for (int rr = grp * RPG; rr < (grp + 1) * RPG; ++rr) {
+              int t_ = tgt[rr];
+              float m = stage[rr * (CH + 1) + ch];
+              if (t_ != cur) {
+                if (cur >= 0) atomicAdd(p.aggr + (size_t)cur * 128 + c0 + sub + ch, acc);
+                cur = t_;
+                acc = 0.f;
+              }
+              acc += m;
+            }
+            if (cur >= 0) atomicAdd(p.aggr + (size_t)cur * 128 + c0 + sub + ch, acc);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  // teardown
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+template <int NSPLIT, int CH>
+static size_t edge_chain_smem() {
+  return 1024 + 3 * NSPLIT * kWBlk + 512 * 4 + 128 * 16 + 8 * 32 * (CH + 1) * 4 + 256 * 4 + 3 * 8 + 16;
+}
+
+size_t edge_chain_pack_bytes(int mode) { return (size_t)3 * (mode == BSMS_MODE_FP16X3 ? 2 : 1) * kWBlk; }
+
+// Packs W2..W4 and runs the fused edge stage.  aggr must be zero-filled by the caller.
+int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* PsPd, const float* pos,
+                       int pos_batched, int B, int P, int mode, uint8_t* wpack, float* aggr, float* dbg, int dbg_stage,
+                       cudaStream_t st) {
+  const long long rows = (long long)B * pl->n_edges;
+  if (rows == 0) return BSMS_OK;
+  PackList pk;
+  pk.n = 3;
+  for (int l = 0; l < 3; ++l) {
+    pk.w[l] = w->w_edge[l + 1];
+    pk.ld[l] = kD;
+  }
+  EdgeChainParams p;
+  p.PsPd = PsPd;
+  p.pos = pos;
+  p.pos_batched = pos_batched;
+  p.P = P;
+  p.src_d = pl->src_d;
+  p.dst_d = pl->dst_d;
+  p.W1 = w->w_edge[0];
+  for (int l = 0; l < 4; ++l) p.b[l] = w->b_edge[l];
+  p.wpack = wpack;
+  p.aggr = aggr;
+  p.B = B;
+  p.N = pl->n_nodes;
+  p.E = pl->n_edges;
+  p.rows = rows;
+  p.ntiles = ceil_div(rows, 128);
+  p.dbg = dbg;
+  p.dbg_stage = dbg_stage;
+  int dev = 0, sms = 148;
+  BSMS_CUDA(cudaGetDevice(&dev));
+  BSMS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = std::min(sms, ceil_div(p.ntiles, 2));
+  if (mode == BSMS_MODE_BF16) {
+    {
+      ProfScope ps_(PK_OTHER, st);
+      k_pack_weights<1><<<3, 256, 0, st>>>(pk, wpack);
+      BSMS_LAUNCHED();
+    }
+    auto kern = k_edge_chain<1, 32>;
+    const size_t smem = edge_chain_smem<1, 32>();
+    BSMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps_(PK_EDGE_FWD_GEMM, st);
+    kern<<<grid, 256, smem, st>>>(p);
+    BSMS_LAUNCHED();
+  } else {
+    {
+      ProfScope ps_(PK_OTHER, st);
+      k_pack_weights<2><<<3, 256, 0, st>>>(pk, wpack);
+      BSMS_LAUNCHED();
+    }
+    auto kern = k_edge_chain<2, 16>;
+    const size_t smem = edge_chain_smem<2, 16>();
+    BSMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps_(PK_EDGE_FWD_GEMM, st);
+    kern<<<grid, 256, smem, st>>>(p);
+    BSMS_LAUNCHED();
+  }
+  return BSMS_OK;
+}
+
+}  // namespace bsms

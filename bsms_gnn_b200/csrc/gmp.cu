@@ -242,8 +242,15 @@ struct Fp32Acts {
   float *PsPd, *A0, *A1, *A2, *Y, *aggr, *N1, *N2, *N3, *Yn;
 };
 
+// fused tcgen05 edge stage (edge_chain.cu)
+size_t edge_chain_pack_bytes(int mode);
+int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* PsPd, const float* pos,
+                       int pos_batched, int B, int P, int mode, uint8_t* wpack, float* aggr, float* dbg, int dbg_stage,
+                       cudaStream_t st);
+
 static int fp32_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos,
-                        int pos_batched, int B, int P, const Fp32Acts& a, cudaStream_t st) {
+                        int pos_batched, int B, int P, const Fp32Acts& a, cudaStream_t st, int mode = BSMS_MODE_FP32,
+                        uint8_t* wpack = nullptr) {
   const int N = pl->n_nodes, E = pl->n_edges;
   const long long Rn = (long long)B * N, Re = (long long)B * E;
   const int ldw1 = 2 * D + P + 1;
@@ -251,7 +258,11 @@ static int fp32_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, co
   BSMS_TRY(gemm_nt(x, D, nullptr, 0, D, 0, w->w_edge[0] + (P + 1), ldw1, nullptr, nullptr, 0, a.PsPd, 256, Rn, D, 0, st, PK_NODE_FWD_GEMM));
   BSMS_TRY(gemm_nt(x, D, nullptr, 0, D, 0, w->w_edge[0] + (P + 1 + D), ldw1, nullptr, nullptr, 0, a.PsPd + 128, 256, Rn,
                    D, 0, st, PK_NODE_FWD_GEMM));
-  if (Re > 0) {
+  if (mode != BSMS_MODE_FP32) {
+    // tensor-core modes: the whole edge stage is one fused kernel that reduces into aggr
+    BSMS_CUDA(cudaMemsetAsync(a.aggr, 0, (size_t)Rn * D * sizeof(float), st));
+    BSMS_TRY(edge_chain_forward(pl, w, a.PsPd, pos, pos_batched, B, P, mode, wpack, a.aggr, nullptr, -1, st));
+  } else if (Re > 0) {
     if (P == 1) BSMS_TRY(edge_combine<1>(a.PsPd, pos, pos_batched, pl, w->w_edge[0], w->b_edge[0], a.A0, B, st));
     if (P == 2) BSMS_TRY(edge_combine<2>(a.PsPd, pos, pos_batched, pl, w->w_edge[0], w->b_edge[0], a.A0, B, st));
     if (P == 3) BSMS_TRY(edge_combine<3>(a.PsPd, pos, pos_batched, pl, w->w_edge[0], w->b_edge[0], a.A0, B, st));
@@ -259,11 +270,11 @@ static int fp32_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, co
     BSMS_TRY(gemm_nt(a.A1, D, nullptr, 0, D, 0, w->w_edge[2], D, w->b_edge[2], nullptr, 0, a.A2, D, Re, D, GEMM_RELU, st, PK_EDGE_FWD_GEMM));
     BSMS_TRY(gemm_nt(a.A2, D, nullptr, 0, D, 0, w->w_edge[3], D, w->b_edge[3], nullptr, 0, a.Y, D, Re, D, 0, st, PK_EDGE_FWD_GEMM));
   }
-  {
+  if (mode == BSMS_MODE_FP32) {
     ProfScope ps_(PK_LN_SEGSUM, st);
     k_ln_segsum<<<ceil_div(Rn * 32, 256), 256, 0, st>>>(a.Y, pl->rowptr_d, a.aggr, B, N, E);
+    BSMS_LAUNCHED();
   }
-  BSMS_LAUNCHED();
   BSMS_TRY(gemm_nt(x, D, a.aggr, D, D, D, w->w_node[0], 2 * D, w->b_node[0], nullptr, 0, a.N1, D, Rn, D, GEMM_RELU, st, PK_NODE_FWD_GEMM));
   BSMS_TRY(gemm_nt(a.N1, D, nullptr, 0, D, 0, w->w_node[1], D, w->b_node[1], nullptr, 0, a.N2, D, Rn, D, GEMM_RELU, st, PK_NODE_FWD_GEMM));
   BSMS_TRY(gemm_nt(a.N2, D, nullptr, 0, D, 0, w->w_node[2], D, w->b_node[2], nullptr, 0, a.N3, D, Rn, D, GEMM_RELU, st, PK_NODE_FWD_GEMM));
@@ -302,7 +313,7 @@ extern "C" size_t bsms_gmp_workspace_bytes(int32_t B, int32_t N, int32_t E, int3
   (void)mode;
   size_t Rn = (size_t)B * N, Re = (size_t)B * (E > 0 ? E : 1);
   auto f = [](size_t n) { return align_up(n * sizeof(float), 256); };
-  size_t fwd = f(Rn * 256) + f(Re * D) + 2 * f(Rn * D);
+  size_t fwd = f(Rn * 256) + f(Re * D) + 2 * f(Rn * D) + align_up(edge_chain_pack_bytes(BSMS_MODE_FP16X3), 256);
   if (!backward) return fwd + 4096;
   size_t bwd = f(Rn * 256) + 4 * f(Re * D) + 5 * f(Rn * D)  // kept activations
                + 2 * f(Re * D) + 2 * f(Rn * D) + 2 * f(Rn * 256);  // gradient ping-pong, gcat, gPsPd
@@ -314,7 +325,8 @@ static int check_common(const bsms_level_plan* pl, const bsms_gmp_weights* w, co
   BSMS_CHECK_ARG(pl && w && x && pos, "bsms_gmp: null argument");
   BSMS_CHECK_ARG(B >= 1, "bsms_gmp: B must be >= 1");
   BSMS_CHECK_ARG(P >= 1 && P <= 3, "bsms_gmp: pos_dim %d unsupported (1..3)", P);
-  BSMS_CHECK_ARG(mode == BSMS_MODE_FP32, "bsms_gmp: mode %d not built", mode);
+  BSMS_CHECK_ARG(mode == BSMS_MODE_FP32 || mode == BSMS_MODE_FP16X3 || mode == BSMS_MODE_BF16, "bsms_gmp: unknown mode %d",
+                 mode);
   for (int l = 0; l < 4; ++l)
     BSMS_CHECK_ARG(w->w_edge[l] && w->b_edge[l] && w->w_node[l] && w->b_node[l], "bsms_gmp: null weight %d", l);
   return BSMS_OK;
@@ -333,7 +345,8 @@ extern "C" int bsms_gmp_forward(const bsms_level_plan* pl, const bsms_gmp_weight
   const long long Rn = (long long)B * pl->n_nodes, Re = (long long)B * pl->n_edges;
   Arena ar(ws, ws_bytes);
   Fp32Acts a = carve(ar, Rn, Re, false);
-  BSMS_TRY(fp32_forward(pl, w, x, pos, pos_batched, B, P, a, st));
+  uint8_t* wpack = ar.take<uint8_t>(edge_chain_pack_bytes(BSMS_MODE_FP16X3));
+  BSMS_TRY(fp32_forward(pl, w, x, pos, pos_batched, B, P, a, st, mode, wpack));
   {
     ProfScope ps_(PK_OTHER, st);
     k_ln_residual<<<ceil_div(Rn * 32, 256), 256, 0, st>>>(a.Yn, x, skip, out, Rn);
@@ -416,4 +429,26 @@ extern "C" int bsms_gmp_backward(const bsms_level_plan* pl, const bsms_gmp_weigh
     BSMS_TRY(gemm_kn(gPsPd + 128, 256, D, w->w_edge[0] + (P + 1 + D), ldw1, nullptr, 0, g_x, D, Rn, D, GEMM_ACCUM, st));
   }
   return BSMS_OK;
+}
+
+
+// Test hook: runs the pre-projection and the fused edge stage in `mode` and dumps one intermediate
+// per edge row (dst-sorted order) into dbg [B*E, 128]: stage 0 = a0 (after gather/ReLU),
+// 1, 2 = activations after layers 1, 2, 3 = pre-LayerNorm output of layer 3; aggr receives the result.
+extern "C" int bsms_debug_edge_stage(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x,
+                                     const float* pos, int32_t pos_batched, int32_t B, int32_t P, int32_t mode,
+                                     int32_t stage, float* dbg, float* aggr, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  BSMS_TRY(check_common(pl, w, x, pos, B, P, mode));
+  BSMS_CHECK_ARG(mode != BSMS_MODE_FP32 && dbg && aggr && ws, "bsms_debug_edge_stage: bad argument");
+  const long long Rn = (long long)B * pl->n_nodes;
+  const int ldw1 = 2 * D + P + 1;
+  Arena ar(ws, ws_bytes);
+  float* PsPd = ar.take<float>(Rn * 256);
+  uint8_t* wpack = ar.take<uint8_t>(edge_chain_pack_bytes(BSMS_MODE_FP16X3));
+  BSMS_CHECK_ARG(ar.ok(), "bsms_debug_edge_stage: workspace too small");
+  BSMS_TRY(gemm_nt(x, D, nullptr, 0, D, 0, w->w_edge[0] + (P + 1), ldw1, nullptr, nullptr, 0, PsPd, 256, Rn, D, 0, st));
+  BSMS_TRY(gemm_nt(x, D, nullptr, 0, D, 0, w->w_edge[0] + (P + 1 + D), ldw1, nullptr, nullptr, 0, PsPd + 128, 256, Rn, D, 0, st));
+  BSMS_CUDA(cudaMemsetAsync(aggr, 0, (size_t)Rn * D * sizeof(float), st));
+  return edge_chain_forward(pl, w, PsPd, pos, pos_batched, B, P, mode, wpack, aggr, dbg, stage, st);
 }

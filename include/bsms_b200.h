@@ -155,6 +155,15 @@ int bsms_gmp_backward(const bsms_level_plan* plan, const bsms_gmp_weights* w, co
                       const bsms_gmp_grads* grads, int32_t B, int32_t P, int32_t mode,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Test hook for the fused tcgen05 edge stage (mode FP16X3 or BF16): runs the per-node
+ * pre-projection and the fused kernel and dumps one intermediate per edge row, dst-sorted order,
+ * into dbg [B*E,128]: stage 0 = a0 after gather+ReLU, 1/2 = activations after edge layers 1/2,
+ * 3 = layer-3 output before LayerNorm.  aggr [B*N,128] receives the aggregated messages. */
+int bsms_debug_edge_stage(const bsms_level_plan* plan, const bsms_gmp_weights* w, const float* x,
+                          const float* pos, int32_t pos_batched, int32_t B, int32_t P, int32_t mode,
+                          int32_t stage, float* dbg, float* aggr, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline pass).
  * Kinds: 0 edge-MLP forward GEMM/chain, 1 node-level forward GEMMs, 2 edge gather+combine,
  * 3 LayerNorm+segment-sum, 4 dgrad, 5 wgrad, 6 LayerNorm backward, 7 edge-gradient segment sums,
