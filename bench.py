@@ -249,7 +249,7 @@ def main():
         e2e_s = float(t.item())
 
     # ---- roofline pass: per-kernel CUDA-event timing inside the library (rank 0)
-    roofline, breakdown = None, None
+    roofline, breakdown, roofline_edge = None, None, None
     if rank == 0:
         _lib.prof_enable(True)
         prof_steps = 2
@@ -259,30 +259,55 @@ def main():
         _lib.prof_enable(False)
         pk = peaks()
         Re, Rn = B * edge_rows, B * node_rows
-        # algorithmic FLOPs of each kernel class in ONE fwd+bwd step (backward recomputes the forward)
-        flops = {"edge_fwd_gemm": 2 * Re * 3 * 2 * D * D, "dgrad": (Re * 3 + Rn * 7) * 2 * D * D,
-                 "wgrad": (Re * 3 + Rn * 8) * 2 * D * D, "node_fwd_gemm": 2 * Rn * 7 * 2 * D * D}
-        # gather-counted bytes for the bandwidth kernels
+        tensor_mode = args.mode != "fp32"
+        fwd_passes = 1 if tensor_mode else 2  # fp32 FFMA edge layers also run in backward's recompute
+        # algorithmic work of each kernel class in ONE fwd+bwd step (DESIGN.md "Kernels"):
+        #   FLOPs for the dense kernels, gather-counted bytes for the bandwidth kernels
+        flops = {"edge_fwd_gemm": fwd_passes * Re * 3 * 2 * D * D, "dgrad": (Re * 3 + Rn * 7) * 2 * D * D,
+                 "wgrad": (Re * 3 + Rn * 8) * 2 * D * D, "node_fwd_gemm": 2 * Rn * 7 * 2 * D * D,
+                 "edge_chain": Re * 3 * 2 * D * D}
         byts = {"edge_combine": 2 * (Re * (2 * D * 4 + 16 + 8 + D * 4)), "ln_segsum": 2 * (Re * D * 4 + Rn * D * 4),
-                "ln_bwd": Re * 3 * D * 4 + Rn * 3 * D * 4, "edge_grad_segsum": 2 * Re * D * 4 + Rn * 2 * D * 4}
+                "ln_bwd": Re * 3 * D * 4 + Rn * 3 * D * 4, "edge_grad_segsum": 2 * Re * D * 4 + Rn * 2 * D * 4,
+                "edge_chain": Re * (2 * D * 4 + 2 * 2 * 4 + 2 * 4) + Rn * D * 4}
         breakdown = {k: {"ms_per_step": v[0] / prof_steps, "launches_per_step": v[1] / prof_steps}
                      for k, v in prof.items() if v[1]}
+        total_ms = sum(v["ms_per_step"] for v in breakdown.values())
+
+        def roof(kind):
+            tms = breakdown[kind]["ms_per_step"]
+            r = {"kernel": kind, "share_of_step": tms / total_ms, "traffic": None,
+                 "avg_launch_us": 1e3 * tms / breakdown[kind]["launches_per_step"]}
+            if kind == "edge_chain" and args.mode == "bf16":
+                # 1x bf16 MMA: HBM (gather-counted) is the governing bound, SURVEY.md §8d
+                ach = byts[kind] / (tms * 1e-3) / 1e9
+                r.update(bound="hbm", achieved=ach, peak=pk["hbm_gbs"], unit="GB/s", frac=ach / pk["hbm_gbs"],
+                         peak_source=pk["source"],
+                         tensor_tflops=flops[kind] / (tms * 1e-3) / 1e12)
+            elif kind in flops:
+                ach = flops[kind] / (tms * 1e-3) / 1e12
+                peak = pk["bf16_tflops_sustained"]
+                note = None
+                if kind == "edge_chain":  # fp16x3: every logical MAC costs three fp16 MACs
+                    peak = peak / 3.0
+                    note = "fp16x3 split: peak = measured bf16/fp16 dense peak / 3 (3 MMAs per logical MMA)"
+                elif kind != "edge_chain":
+                    note = "FFMA fp32 kernel; fraction is against the tensor-pipe peak the tcgen05 kernels target"
+                r.update(bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak,
+                         peak_source=pk["source"] + " bf16 sustained", note=note)
+                if kind == "edge_chain":
+                    r["gather_counted_gbs"] = byts[kind] / (tms * 1e-3) / 1e9
+            else:
+                ach = byts.get(kind, 0) / (tms * 1e-3) / 1e9
+                r.update(bound="hbm", achieved=ach, peak=pk["hbm_gbs"], unit="GB/s", frac=ach / pk["hbm_gbs"],
+                         peak_source=pk["source"])
+            return r
+
         top = max(breakdown, key=lambda k: breakdown[k]["ms_per_step"])
-        tms = breakdown[top]["ms_per_step"]
-        if top in flops:
-            ach = flops[top] / (tms * 1e-3) / 1e12
-            peak = pk["bf16_tflops_sustained"]
-            roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                        "frac": ach / peak, "traffic": None, "peak_source": pk["source"] + " bf16 sustained",
-                        "share_of_step": tms / sum(v["ms_per_step"] for v in breakdown.values())}
-            if args.mode == "fp32":
-                roofline["note"] = ("fp32 mode runs the dense layers as FFMA (exact fp32 products); the tensor-pipe "
-                                    "fraction is reported against the bf16 peak for continuity with the tcgen05 modes")
+        roofline = roof(top)
+        if "edge_chain" in breakdown and top != "edge_chain":
+            roofline_edge = roof("edge_chain")
         else:
-            ach = byts.get(top, 0) / (tms * 1e-3) / 1e9
-            roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                        "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
-                        "share_of_step": tms / sum(v["ms_per_step"] for v in breakdown.values())}
+            roofline_edge = None
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
@@ -312,7 +337,7 @@ def main():
                     "h2d_bytes_per_step": int(h_host.numel() * 4 + pos_host.numel() * 4), "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_s * 1e3},
             "gpu_launches": int(launches),
-            "roofline": roofline, "kernel_breakdown": breakdown, "cpu_baseline": cpu,
+            "roofline": roofline, "roofline_fused_edge_kernel": roofline_edge, "kernel_breakdown": breakdown, "cpu_baseline": cpu,
         }
         print(json.dumps(out))
     if world > 1:

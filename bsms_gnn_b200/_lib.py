@@ -124,7 +124,7 @@ def workspace(nbytes: int, device) -> torch.Tensor:
 
 
 PROF_KINDS = ["edge_fwd_gemm", "node_fwd_gemm", "edge_combine", "ln_segsum", "dgrad", "wgrad", "ln_bwd",
-              "edge_grad_segsum", "transfer", "other"]
+              "edge_grad_segsum", "transfer", "other", "edge_chain", "edge_chain_bwd"]
 
 
 def prof_enable(on: bool):

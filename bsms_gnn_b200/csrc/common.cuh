@@ -48,7 +48,9 @@ enum ProfKind {
   PK_EDGE_GRAD_SEGSUM = 7,
   PK_TRANSFER = 8,  // restriction / prolongation / conv
   PK_OTHER = 9,
-  PK_COUNT = 10
+  PK_EDGE_CHAIN = 10,  // fused tcgen05 edge stage (gather -> 3 UMMA layers -> LN -> segmented reduce)
+  PK_EDGE_CHAIN_BWD = 11,  // fused tcgen05 backward of the edge stage
+  PK_COUNT = 12
 };
 bool prof_enabled();
 void prof_begin(int kind, cudaStream_t st);

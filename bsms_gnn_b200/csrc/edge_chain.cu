@@ -17,48 +17,10 @@
 // accumulator is rescaled by 2^-12 in the epilogue.
 #include "common.cuh"
 #include "umma.cuh"
+#include "chain.cuh"
 
 namespace bsms {
 using namespace umma;
-
-constexpr int kD = BSMS_LATENT;
-constexpr uint32_t kWBlk = 128 * 128 * 2;  // one packed 128x128 16-bit operand block (32 KB)
-constexpr float kActScale = 16.f;          // 2^4
-constexpr float kWScale = 256.f;           // 2^8
-
-// byte offset of element (n, k) inside a packed block = its shared-memory image
-__host__ __device__ inline uint32_t wblk_offset(int n, int k) {
-  return (uint32_t)((k >> 6) * 16384 + n * 128 + ((((k & 63) >> 3) ^ (n & 7)) << 4) + (k & 7) * 2);
-}
-
-struct PackList {
-  const float* w[8];
-  int ld[8];
-  int n;
-};
-
-// fp32 [128 x 128] (row n, ld) -> packed 16-bit block(s).  grid = (n_blocks), block = 256
-template <int NSPLIT>
-__global__ void k_pack_weights(PackList pl, uint8_t* __restrict__ out) {
-  const int blk = blockIdx.x;
-  const float* W = pl.w[blk];
-  const int ld = pl.ld[blk];
-  uint8_t* o = out + (size_t)blk * NSPLIT * kWBlk;
-  for (int idx = threadIdx.x; idx < 128 * 128; idx += blockDim.x) {
-    int n = idx >> 7, k = idx & 127;
-    float v = W[(size_t)n * ld + k];
-    uint32_t off = wblk_offset(n, k);
-    if (NSPLIT == 1) {
-      *reinterpret_cast<__nv_bfloat16*>(o + off) = __float2bfloat16_rn(v);
-    } else {
-      float s = v * kWScale;
-      __half hi = __float2half_rn(s);
-      __half lo = __float2half_rn(s - __half2float(hi));
-      *reinterpret_cast<__half*>(o + off) = hi;
-      *reinterpret_cast<__half*>(o + kWBlk + off) = lo;
-    }
-  }
-}
 
 struct EdgeChainParams {
   const float* PsPd;  // [B*N, 256]
@@ -366,7 +328,7 @@ int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, con
     auto kern = k_edge_chain<1, 32>;
     const size_t smem = edge_chain_smem<1, 32>();
     BSMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ProfScope ps_(PK_EDGE_FWD_GEMM, st);
+    ProfScope ps_(PK_EDGE_CHAIN, st);
     kern<<<grid, 256, smem, st>>>(p);
     BSMS_LAUNCHED();
   } else {
@@ -378,7 +340,7 @@ int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, con
     auto kern = k_edge_chain<2, 16>;
     const size_t smem = edge_chain_smem<2, 16>();
     BSMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ProfScope ps_(PK_EDGE_FWD_GEMM, st);
+    ProfScope ps_(PK_EDGE_CHAIN, st);
     kern<<<grid, 256, smem, st>>>(p);
     BSMS_LAUNCHED();
   }

@@ -1,0 +1,445 @@
+// Fused backward of the GMP edge stage on tcgen05 (bf16 operands, fp32 accumulate), by
+// recomputation: nothing per-edge is read from or written to HBM except the gathers of the
+// projected node rows / upstream gradient rows and the scatter of the edge-input gradient.
+//
+// Per 128-edge tile (one tile per CTA at a time, persistent grid, 256 threads = 2 threads per edge
+// row: thread (row r, half h) owns channels [64h, 64h+64) of TMEM lane r):
+//   a0 = relu(Ps[src]+Pd[dst]+b1+F fiber)            gather            -> T0 (bf16 smem tile), mask m0
+//   a1 = relu(a0 W2^T + b2)                           UMMA  D=T0 x W2   -> T1, m1
+//   a2 = relu(a1 W3^T + b3)                           UMMA  D=T1 x W3   -> T2, m2
+//   y  = a2 W4^T + b4 ; gy = LN'(y) * g_aggr[dst]     UMMA  D=T2 x W4   -> T0 (a0 is re-gathered later)
+//   dW4 += gy^T a2 ; g2 = (gy W4) . m2                UMMA  wgrad(T0,T2), dgrad D=T0 x W4(MN)  -> T2
+//   dW3 += g2^T a1 ; g1 = (g2 W3) . m1                UMMA  wgrad(T2,T1), dgrad D=T2 x W3(MN)  -> T1 ; a0 -> T0
+//   dW2 += g1^T a0 ; g0 = (g1 W2) . m0                UMMA  wgrad(T1,T0), dgrad D=T1 x W2(MN)
+//   gPs[src] += g0 ; gPd[dst] += g0 (red.add.v4) ; gF += g0^T fiber ; gb* += column sums
+// The three weight-gradient accumulators (3 x 128 TMEM columns) stay resident in tensor memory for
+// the whole persistent loop and are reduced into global memory once per CTA; the activation /
+// gradient tiles are written once in the canonical 128B-swizzled layout and consumed BOTH as
+// K-major operands (forward / data-gradient GEMMs) and as MN-major operands (weight-gradient
+// GEMMs) by re-describing the same bytes.  Weights are staged once per CTA by cp.async.bulk and
+// read K-major (recompute) and MN-major (= W^T, data gradient) from the same image.
+#include "chain.cuh"
+
+namespace bsms {
+
+struct EdgeBwdParams {
+  const float* PsPd;  // [B*N, 256]
+  const float* pos;
+  int pos_batched, P;
+  const int32_t* src_d;
+  const int32_t* dst_d;
+  const float* W1;
+  const float* b[4];
+  const uint8_t* wpack;  // [3] packed bf16 blocks (W2, W3, W4)
+  const float* g_aggr;   // upstream gradient of aggr, row stride ld_g
+  int ld_g;
+  float* gPsPd;  // [B*N, 256], zero-initialised; receives gPs | gPd
+  float* gW[3];  // W2, W3, W4 gradients [128,128] (accumulated)
+  float* gb[4];  // b1..b4 gradients
+  float* gW1;    // mlp_edge layer-0 weight gradient [128, 2*128+P+1]: fiber columns accumulated here
+  int B, N, E;
+  long long rows;
+  int ntiles;
+};
+
+__device__ __forceinline__ uint32_t tile_off(int r, int chunk) {  // 16-byte chunk `chunk` (0..15) of row r
+  return (uint32_t)((chunk >> 3) * 16384 + r * 128 + (((chunk & 7) ^ (r & 7)) << 4));
+}
+
+// 64 fp32 values (channels 64h..64h+63 of row r) -> bf16 -> tile
+__device__ __forceinline__ void store_tile64(uint8_t* tile, int r, int h, const float (&v)[64]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint4 u;
+    u.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+    u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+    u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+    u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+    *reinterpret_cast<uint4*>(tile + tile_off(r, 8 * h + j)) = u;
+  }
+}
+
+__device__ __forceinline__ float tile_elem(const uint8_t* tile, int r, int c) {
+  const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(tile + tile_off(r, c >> 3) + (c & 7) * 2);
+  return __bfloat162float(*p);
+}
+
+__device__ __forceinline__ void load_d64(uint32_t taddr, float (&v)[64]) {
+  uint32_t r0[32], r1[32];
+  tmem_ld32(taddr, r0);
+  tmem_ld32(taddr + 32, r1);
+  wait_ld();
+#pragma unroll
+  for (int t = 0; t < 32; ++t) {
+    v[t] = __uint_as_float(r0[t]);
+    v[32 + t] = __uint_as_float(r1[t]);
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t IDESC_KK = make_idesc(1, 128, 128, 0, 0);  // A K-major, B K-major   (recompute)
+  constexpr uint32_t IDESC_KM = make_idesc(1, 128, 128, 0, 1);  // A K-major, B MN-major  (dgrad: B = W^T)
+  constexpr uint32_t IDESC_MM = make_idesc(1, 128, 128, 1, 1);  // A, B MN-major          (wgrad)
+  const uint32_t s0 = smem_u32(smem_raw);
+  const uint32_t sbase = (s0 + 1023u) & ~1023u;
+  uint8_t* sp = smem_raw + (sbase - s0);
+  uint8_t* s_T[3] = {sp + 3 * kWBlk, sp + 4 * kWBlk, sp + 5 * kWBlk};
+  float* s_bias = reinterpret_cast<float*>(sp + 6 * kWBlk);  // [4][128]
+  float4* s_F = reinterpret_cast<float4*>(s_bias + 512);     // [128]
+  float4* s_fib = s_F + 128;                                 // [128] fiber of each tile row
+  float4* s_x = s_fib + 128;                                 // [2][128] LayerNorm partial sums
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_x + 256);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
+  const uint32_t aW[3] = {sbase, sbase + kWBlk, sbase + 2 * kWBlk};
+  const uint32_t aT[3] = {sbase + 3 * kWBlk, sbase + 4 * kWBlk, sbase + 5 * kWBlk};
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, h = warp >> 2, r = q * 32 + lane;
+  const uint32_t bar_w = smem_u32(&s_bar[0]), bar_m = smem_u32(&s_bar[1]);
+
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_m, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
+  for (int i = tid; i < 512; i += 256) s_bias[i] = p.b[i >> 7][i & 127];
+  {
+    const int ldw1 = 2 * kD + p.P + 1;
+    for (int c = tid; c < 128; c += 256) {
+      float f[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int k = 0; k <= p.P; ++k) f[k] = p.W1[(size_t)c * ldw1 + k];
+      s_F[c] = make_float4(f[0], f[1], f[2], f[3]);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+  if (tid == 0) {
+    mbar_expect_tx(bar_w, 3 * kWBlk);
+    for (int blk = 0; blk < 3; ++blk) bulk_g2s(aW[blk], p.wpack + (size_t)blk * kWBlk, kWBlk, bar_w);
+    mbar_wait(bar_w, 0);
+  }
+  const uint32_t d_tmem = tmem_base;  // D: cols [0,128); dW2/dW3/dW4: cols [128,256), [256,384), [384,512)
+  const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+  const uint32_t d_mine = d_tmem + lane_off + 64 * h;
+  uint32_t phase = 0;
+  uint32_t wacc = 0;  // weight-gradient accumulators hold something
+  // persistent per-thread partial sums for the bias / fiber-weight gradients (channel cc, row half rh)
+  const int cc = tid & 127, rh = tid >> 7;
+  float acc_b[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc_f[4] = {0.f, 0.f, 0.f, 0.f};
+
+  // one full-CTA phase boundary: make generic smem writes visible to the tensor core, order tcgen05 ops
+  auto sync_all = [&]() {
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+  };
+  auto wait_mma = [&]() {
+    mbar_wait(bar_m, phase);
+    phase ^= 1;
+    fence_after_sync();
+  };
+  // D = A(tile, K-major) x B(weight block): K-major B for the recompute, MN-major B (= W^T) for dgrad
+  auto issue_gemm = [&](uint32_t a_tile, uint32_t b_blk, bool b_mn) {
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const uint64_t ad = smem_desc_sw128(a_tile + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
+      const uint64_t bd = b_mn ? smem_desc_sw128(b_blk + ks * 2048, 16384, 1024)
+                               : smem_desc_sw128(b_blk + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
+      mma_ss(d_tmem, ad, bd, b_mn ? IDESC_KM : IDESC_KK, ks > 0);
+    }
+  };
+  // dW[out][in] += G^T A : both operands MN-major views of [row][channel] tiles, K = 128 tile rows
+  auto issue_wgrad = [&](uint32_t dw_tmem, uint32_t g_tile, uint32_t a_tile) {
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const uint64_t ad = smem_desc_sw128(g_tile + ks * 2048, 16384, 1024);
+      const uint64_t bd = smem_desc_sw128(a_tile + ks * 2048, 16384, 1024);
+      mma_ss(dw_tmem, ad, bd, IDESC_MM, (wacc | ks) != 0);
+    }
+  };
+  // column sums of a gradient tile (bias gradient) by channel-owner threads; overlaps the MMAs
+  auto colsum = [&](const uint8_t* tile, float& acc) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int rr = rh * 64; rr < rh * 64 + 64; ++rr) s += tile_elem(tile, rr, cc);
+    acc += s;
+  };
+
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    const long long row = (long long)tile * 128 + r;
+    const bool valid = row < p.rows;
+    int b = 0, i = 0, j = 0;
+    if (valid) {
+      b = (int)(row / p.E);
+      int e = (int)(row - (long long)b * p.E);
+      i = p.src_d[e];
+      j = p.dst_d[e];
+    }
+    float fib[4] = {0.f, 0.f, 0.f, 0.f};
+    if (valid) {
+      const float* pb = p.pos + (p.pos_batched ? (size_t)b * p.N * p.P : 0);
+      float nrm = 0.f;
+      for (int k = 0; k < p.P; ++k) {
+        float dlt = pb[(size_t)i * p.P + k] - pb[(size_t)j * p.P + k];
+        fib[k] = dlt;
+        nrm += dlt * dlt;
+      }
+      fib[p.P] = sqrtf(nrm);
+    }
+    if (h == 0) s_fib[r] = make_float4(fib[0], fib[1], fib[2], fib[3]);
+    const float* ps_row = p.PsPd + ((size_t)b * p.N + i) * 256 + 64 * h;
+    const float* pd_row = p.PsPd + ((size_t)b * p.N + j) * 256 + 128 + 64 * h;
+    uint32_t m0[2] = {0u, 0u}, m1[2] = {0u, 0u}, m2[2] = {0u, 0u};
+
+    // a0 (gather) -> dst tile; returns the ReLU mask
+    auto gather_a0 = [&](uint8_t* dst_tile, uint32_t (&mask)[2]) {
+      float v[64];
+#pragma unroll
+      for (int q4 = 0; q4 < 16; ++q4) {
+        float4 a = valid ? ld4(ps_row + q4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 d = valid ? ld4(pd_row + q4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[q4 * 4 + 0] = a.x + d.x; v[q4 * 4 + 1] = a.y + d.y; v[q4 * 4 + 2] = a.z + d.z; v[q4 * 4 + 3] = a.w + d.w;
+      }
+      mask[0] = mask[1] = 0u;
+#pragma unroll
+      for (int t = 0; t < 64; ++t) {
+        const int c = 64 * h + t;
+        float4 f = s_F[c];
+        float x = v[t] + s_bias[c] + f.x * fib[0] + f.y * fib[1] + f.z * fib[2] + f.w * fib[3];
+        const bool on = valid && x > 0.f;
+        v[t] = on ? x : 0.f;
+        mask[t >> 5] |= (on ? 1u : 0u) << (t & 31);
+      }
+      store_tile64(dst_tile, r, h, v);
+    };
+    // activation epilogue: D + bias -> ReLU -> tile, mask
+    auto act_epilogue = [&](const float* bias, uint8_t* dst_tile, uint32_t (&mask)[2]) {
+      float v[64];
+      load_d64(d_mine, v);
+      mask[0] = mask[1] = 0u;
+#pragma unroll
+      for (int t = 0; t < 64; ++t) {
+        float x = v[t] + bias[64 * h + t];
+        const bool on = x > 0.f;
+        v[t] = on ? x : 0.f;
+        mask[t >> 5] |= (on ? 1u : 0u) << (t & 31);
+      }
+      store_tile64(dst_tile, r, h, v);
+    };
+    // gradient epilogue: D . mask -> tile
+    auto grad_epilogue = [&](const uint32_t (&mask)[2], uint8_t* dst_tile) {
+      float v[64];
+      load_d64(d_mine, v);
+#pragma unroll
+      for (int t = 0; t < 64; ++t) v[t] = ((mask[t >> 5] >> (t & 31)) & 1u) ? v[t] : 0.f;
+      store_tile64(dst_tile, r, h, v);
+    };
+
+    // ---- recompute the forward chain
+    gather_a0(s_T[0], m0);
+    sync_all();
+    if (tid == 0) {
+      issue_gemm(aT[0], aW[0], false);
+      mma_commit(bar_m);
+    }
+    wait_mma();
+    act_epilogue(s_bias + 128, s_T[1], m1);
+    sync_all();
+    if (tid == 0) {
+      issue_gemm(aT[1], aW[1], false);
+      mma_commit(bar_m);
+    }
+    wait_mma();
+    act_epilogue(s_bias + 256, s_T[2], m2);
+    sync_all();
+    if (tid == 0) {
+      issue_gemm(aT[2], aW[2], false);
+      mma_commit(bar_m);
+    }
+    wait_mma();
+    // ---- LayerNorm backward: gy = rstd * (g - mean(g) - yhat * mean(g * yhat)) -> T0
+    {
+      float y[64], g[64];
+      load_d64(d_mine, y);
+      const float* grow = p.g_aggr + ((size_t)b * p.N + j) * p.ld_g + 64 * h;
+      float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
+#pragma unroll
+      for (int q4 = 0; q4 < 16; ++q4) {
+        float4 gv = valid ? ld4(grow + q4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        g[q4 * 4 + 0] = gv.x; g[q4 * 4 + 1] = gv.y; g[q4 * 4 + 2] = gv.z; g[q4 * 4 + 3] = gv.w;
+      }
+#pragma unroll
+      for (int t = 0; t < 64; ++t) {
+        y[t] += s_bias[384 + 64 * h + t];
+        s1 += y[t];
+        s2 += y[t] * y[t];
+        s3 += g[t];
+        s4 += g[t] * y[t];
+      }
+      s_x[h * 128 + r] = make_float4(s1, s2, s3, s4);
+      __syncthreads();
+      const float4 o = s_x[(1 - h) * 128 + r];
+      s1 += o.x; s2 += o.y; s3 += o.z; s4 += o.w;
+      const float mean = s1 * (1.f / 128.f);
+      const float var = fmaxf(s2 * (1.f / 128.f) - mean * mean, 0.f);
+      const float rstd = 1.f / sqrtf(var + 1e-5f);
+      const float c1 = s3 * (1.f / 128.f);
+      const float c2 = rstd * (s4 - mean * s3) * (1.f / 128.f);
+#pragma unroll
+      for (int t = 0; t < 64; ++t) {
+        const float yh = (y[t] - mean) * rstd;
+        y[t] = valid ? rstd * (g[t] - c1 - yh * c2) : 0.f;
+      }
+      store_tile64(s_T[0], r, h, y);
+    }
+    sync_all();
+    if (tid == 0) {
+      issue_wgrad(tmem_base + 384, aT[0], aT[2]);  // dW4 += gy^T a2
+      issue_gemm(aT[0], aW[2], true);              // D = gy W4
+      mma_commit(bar_m);
+    }
+    colsum(s_T[0], acc_b[3]);
+    wait_mma();
+    grad_epilogue(m2, s_T[2]);  // g2 -> T2
+    sync_all();
+    if (tid == 0) {
+      issue_wgrad(tmem_base + 256, aT[2], aT[1]);  // dW3 += g2^T a1
+      issue_gemm(aT[2], aW[1], true);              // D = g2 W3
+      mma_commit(bar_m);
+    }
+    colsum(s_T[2], acc_b[2]);
+    {
+      uint32_t mtmp[2];
+      gather_a0(s_T[0], mtmp);  // a0 again (T0 was reused for gy)
+    }
+    wait_mma();
+    grad_epilogue(m1, s_T[1]);  // g1 -> T1
+    sync_all();
+    if (tid == 0) {
+      issue_wgrad(tmem_base + 128, aT[1], aT[0]);  // dW2 += g1^T a0
+      issue_gemm(aT[1], aW[0], true);              // D = g1 W2
+      mma_commit(bar_m);
+      wacc = 1;
+    }
+    colsum(s_T[1], acc_b[1]);
+    wait_mma();
+    // ---- g0 = D . m0 : scatter to the projected-row gradients, stage in T2 for gb1 / gF
+    {
+      float v[64];
+      load_d64(d_mine, v);
+#pragma unroll
+      for (int t = 0; t < 64; ++t) v[t] = ((m0[t >> 5] >> (t & 31)) & 1u) ? v[t] : 0.f;
+      if (valid) {
+        float* gs = p.gPsPd + ((size_t)b * p.N + i) * 256 + 64 * h;
+        float* gd = p.gPsPd + ((size_t)b * p.N + j) * 256 + 128 + 64 * h;
+#pragma unroll
+        for (int q4 = 0; q4 < 16; ++q4) {
+          red_add_v4(gs + q4 * 4, v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
+          red_add_v4(gd + q4 * 4, v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
+        }
+      }
+      store_tile64(s_T[2], r, h, v);
+    }
+    __syncthreads();
+    {
+      float sb = 0.f, sf0 = 0.f, sf1 = 0.f, sf2 = 0.f, sf3 = 0.f;
+#pragma unroll 8
+      for (int rr = rh * 64; rr < rh * 64 + 64; ++rr) {
+        const float gv = tile_elem(s_T[2], rr, cc);
+        const float4 f = s_fib[rr];
+        sb += gv;
+        sf0 += gv * f.x; sf1 += gv * f.y; sf2 += gv * f.z; sf3 += gv * f.w;
+      }
+      acc_b[0] += sb;
+      acc_f[0] += sf0; acc_f[1] += sf1; acc_f[2] += sf2; acc_f[3] += sf3;
+    }
+    __syncthreads();  // T2 / s_fib are rewritten by the next tile
+  }
+
+  // ---- flush: weight-gradient accumulators (TMEM) and the per-thread bias / fiber partial sums
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  {
+#pragma unroll 1
+    for (int l = 0; l < 3; ++l) {
+      float v[64];
+      load_d64(tmem_base + 128 * (l + 1) + lane_off + 64 * h, v);
+      float* dst = p.gW[l] + (size_t)r * 128 + 64 * h;  // TMEM lane = output channel
+#pragma unroll
+      for (int q4 = 0; q4 < 16; ++q4) red_add_v4(dst + q4 * 4, v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
+    }
+  }
+#pragma unroll
+  for (int l = 0; l < 4; ++l) atomicAdd(p.gb[l] + cc, acc_b[l]);
+  {
+    const int ldw1 = 2 * kD + p.P + 1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k <= p.P) atomicAdd(p.gW1 + (size_t)cc * ldw1 + k, acc_f[k]);
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+size_t edge_chain_bwd_smem() { return 1024 + 6 * kWBlk + 512 * 4 + 128 * 16 * 2 + 256 * 16 + 2 * 8 + 16; }
+
+// Fused bf16 backward of the edge stage.  gPsPd must be zero-filled; gW/gb/gW1 are accumulated into.
+int edge_chain_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const bsms_gmp_grads* gr, const float* PsPd,
+                        const float* pos, int pos_batched, int B, int P, uint8_t* wpack, const float* g_aggr, int ld_g,
+                        float* gPsPd, cudaStream_t st) {
+  const long long rows = (long long)B * pl->n_edges;
+  if (rows == 0) return BSMS_OK;
+  PackList pk;
+  pk.n = 3;
+  for (int l = 0; l < 3; ++l) {
+    pk.w[l] = w->w_edge[l + 1];
+    pk.ld[l] = kD;
+  }
+  EdgeBwdParams p;
+  p.PsPd = PsPd;
+  p.pos = pos;
+  p.pos_batched = pos_batched;
+  p.P = P;
+  p.src_d = pl->src_d;
+  p.dst_d = pl->dst_d;
+  p.W1 = w->w_edge[0];
+  for (int l = 0; l < 4; ++l) {
+    p.b[l] = w->b_edge[l];
+    p.gb[l] = gr->b_edge[l];
+  }
+  for (int l = 0; l < 3; ++l) p.gW[l] = gr->w_edge[l + 1];
+  p.gW1 = gr->w_edge[0];
+  p.wpack = wpack;
+  p.g_aggr = g_aggr;
+  p.ld_g = ld_g;
+  p.gPsPd = gPsPd;
+  p.B = B;
+  p.N = pl->n_nodes;
+  p.E = pl->n_edges;
+  p.rows = rows;
+  p.ntiles = ceil_div(rows, 128);
+  int dev = 0, sms = 148;
+  BSMS_CUDA(cudaGetDevice(&dev));
+  BSMS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  {
+    ProfScope ps_(PK_OTHER, st);
+    k_pack_weights<1><<<3, 256, 0, st>>>(pk, wpack);
+    BSMS_LAUNCHED();
+  }
+  const size_t smem = edge_chain_bwd_smem();
+  BSMS_CUDA(cudaFuncSetAttribute(k_edge_chain_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope ps_(PK_EDGE_CHAIN_BWD, st);
+  k_edge_chain_bwd<<<std::min(sms, p.ntiles), 256, smem, st>>>(p);
+  BSMS_LAUNCHED();
+  return BSMS_OK;
+}
+
+}  // namespace bsms

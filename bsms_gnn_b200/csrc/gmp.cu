@@ -248,6 +248,10 @@ int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, con
                        int pos_batched, int B, int P, int mode, uint8_t* wpack, float* aggr, float* dbg, int dbg_stage,
                        cudaStream_t st);
 
+int edge_chain_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const bsms_gmp_grads* gr, const float* PsPd,
+                        const float* pos, int pos_batched, int B, int P, uint8_t* wpack, const float* g_aggr, int ld_g,
+                        float* gPsPd, cudaStream_t st);
+
 static int fp32_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos,
                         int pos_batched, int B, int P, const Fp32Acts& a, cudaStream_t st, int mode = BSMS_MODE_FP32,
                         uint8_t* wpack = nullptr) {
@@ -282,12 +286,17 @@ static int fp32_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, co
   return BSMS_OK;
 }
 
-static Fp32Acts carve(Arena& ar, long long Rn, long long Re, bool keep) {
+static Fp32Acts carve(Arena& ar, long long Rn, long long Re, bool keep, bool edge_bufs = true) {
   Fp32Acts a;
   long long re = Re > 0 ? Re : 1;
   a.PsPd = ar.take<float>(Rn * 256);
-  a.A0 = ar.take<float>(re * D);
-  if (keep) {
+  if (!edge_bufs) {
+    a.A0 = a.A1 = a.A2 = a.Y = nullptr;  // the fused tcgen05 kernels keep every per-edge tensor on chip
+  } else {
+    a.A0 = ar.take<float>(re * D);
+  }
+  if (!edge_bufs) {
+  } else if (keep) {
     a.A1 = ar.take<float>(re * D);
     a.A2 = ar.take<float>(re * D);
     a.Y = ar.take<float>(re * D);
@@ -315,7 +324,7 @@ extern "C" size_t bsms_gmp_workspace_bytes(int32_t B, int32_t N, int32_t E, int3
   auto f = [](size_t n) { return align_up(n * sizeof(float), 256); };
   size_t fwd = f(Rn * 256) + f(Re * D) + 2 * f(Rn * D) + align_up(edge_chain_pack_bytes(BSMS_MODE_FP16X3), 256);
   if (!backward) return fwd + 4096;
-  size_t bwd = f(Rn * 256) + 4 * f(Re * D) + 5 * f(Rn * D)  // kept activations
+  size_t bwd = f(Rn * 256) + 4 * f(Re * D) + 5 * f(Rn * D) + align_up(edge_chain_pack_bytes(BSMS_MODE_FP16X3), 256)
                + 2 * f(Re * D) + 2 * f(Rn * D) + 2 * f(Rn * 256);  // gradient ping-pong, gcat, gPsPd
   return bwd + 4096;
 }
@@ -371,15 +380,17 @@ extern "C" int bsms_gmp_backward(const bsms_level_plan* pl, const bsms_gmp_weigh
   const long long Rn = (long long)B * N, Re = (long long)B * E;
   const int ldw1 = 2 * D + P + 1;
   Arena ar(ws, ws_bytes);
-  Fp32Acts a = carve(ar, Rn, Re, true);
-  float* Ge1 = ar.take<float>((Re > 0 ? Re : 1) * D);
-  float* Ge2 = ar.take<float>((Re > 0 ? Re : 1) * D);
+  const bool fused = (mode == BSMS_MODE_BF16);  // fused tcgen05 edge backward; the split modes use the fp32 path
+  Fp32Acts a = carve(ar, Rn, Re, true, !fused);
+  float* Ge1 = fused ? nullptr : ar.take<float>((Re > 0 ? Re : 1) * D);
+  float* Ge2 = fused ? nullptr : ar.take<float>((Re > 0 ? Re : 1) * D);
+  uint8_t* wpack = ar.take<uint8_t>(edge_chain_pack_bytes(BSMS_MODE_FP16X3));
   float* Gn1 = ar.take<float>(Rn * D);
   float* Gn2 = ar.take<float>(Rn * D);
   float* gcat = ar.take<float>(Rn * 256);
   float* gPsPd = ar.take<float>(Rn * 256);
-  // ---- recompute forward, keeping every activation
-  BSMS_TRY(fp32_forward(pl, w, x, pos, pos_batched, B, P, a, st));
+  // ---- recompute forward, keeping every (node-level) activation
+  BSMS_TRY(fp32_forward(pl, w, x, pos, pos_batched, B, P, a, st, fused ? BSMS_MODE_BF16 : BSMS_MODE_FP32, wpack));
   // ---- node MLP backward
   {
     ProfScope ps_(PK_LN_BWD, st);
@@ -402,7 +413,10 @@ extern "C" int bsms_gmp_backward(const bsms_level_plan* pl, const bsms_gmp_weigh
   }
   BSMS_LAUNCHED();
   // ---- edge MLP backward (upstream of edge row e is g_aggr[dst_e] = gcat[:, 128:])
-  if (Re > 0) {
+  if (Re > 0 && fused) {
+    BSMS_CUDA(cudaMemsetAsync(gPsPd, 0, (size_t)Rn * 256 * sizeof(float), st));
+    BSMS_TRY(edge_chain_backward(pl, w, gr, a.PsPd, pos, pos_batched, B, P, wpack, gcat + 128, 256, gPsPd, st));
+  } else if (Re > 0) {
     {
       ProfScope ps_(PK_LN_BWD, st);
       k_ln_bwd<<<ceil_div(Re * 32, 256), 256, 0, st>>>(a.Y, gcat + 128, 256, pl->dst_d, E, N, Ge1, Re);
@@ -422,6 +436,8 @@ extern "C" int bsms_gmp_backward(const bsms_level_plan* pl, const bsms_gmp_weigh
       k_edge_grad_segsum<<<ceil_div(Rn * 32, 256), 256, 0, st>>>(Ge2, pl->rowptr_d, pl->rowptr_s, pl->s2d, gPsPd, B, N, E);
     }
     BSMS_LAUNCHED();
+  }
+  if (Re > 0) {
     // node-level layer-0 gradients: gW1s += gPs^T x, gW1d += gPd^T x, g_x += gPs W1s + gPd W1d
     BSMS_TRY(wgrad(gPsPd, 256, x, D, gr->w_edge[0] + (P + 1), ldw1, nullptr, Rn, st));
     BSMS_TRY(wgrad(gPsPd + 128, 256, x, D, gr->w_edge[0] + (P + 1 + D), ldw1, nullptr, Rn, st));

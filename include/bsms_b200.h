@@ -167,8 +167,9 @@ int bsms_debug_edge_stage(const bsms_level_plan* plan, const bsms_gmp_weights* w
 /* Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline pass).
  * Kinds: 0 edge-MLP forward GEMM/chain, 1 node-level forward GEMMs, 2 edge gather+combine,
  * 3 LayerNorm+segment-sum, 4 dgrad, 5 wgrad, 6 LayerNorm backward, 7 edge-gradient segment sums,
- * 8 transfer (restriction/prolongation/conv), 9 other.  Host pointers; collect synchronises. */
-#define BSMS_PROF_KINDS 10
+ * 8 transfer (restriction/prolongation/conv), 9 other, 10 fused tcgen05 edge stage, 11 its fused backward.
+ * Host pointers; collect synchronises. */
+#define BSMS_PROF_KINDS 12
 int bsms_prof_enable(int on);
 int bsms_prof_collect(double* ms_by_kind_host, int64_t* launches_by_kind_host, int n_kinds);
 
