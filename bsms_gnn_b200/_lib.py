@@ -36,7 +36,7 @@ class GmpWeightsC(C.Structure):
 EXPORTS = [
     "bsms_last_error", "bsms_version", "bsms_device_info", "bsms_plan_workspace_bytes", "bsms_plan_build",
     "bsms_cal_ew", "bsms_permute_ew", "bsms_edge_conv", "bsms_conv_down_pool", "bsms_unpool_conv_up",
-    "bsms_gather_rows", "bsms_unpool_rows", "bsms_gmp_workspace_bytes", "bsms_gmp_forward",
+    "bsms_gather_rows", "bsms_unpool_rows", "bsms_gmp_workspace_bytes", "bsms_gmp_saved_bytes", "bsms_gmp_forward",
     "bsms_gmp_backward", "bsms_launch_count", "bsms_prof_enable", "bsms_prof_collect",
     "bsms_debug_edge_stage",
 ]
@@ -66,8 +66,10 @@ def _load():
     lib.bsms_unpool_rows.argtypes = [vp, vp, i32, i32, vp, i32, i32, vp]
     lib.bsms_gmp_workspace_bytes.restype = sz
     lib.bsms_gmp_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
-    lib.bsms_gmp_forward.argtypes = [P(LevelPlanC), P(GmpWeightsC), vp, vp, i32, vp, vp, i32, i32, i32, vp, sz, vp]
-    lib.bsms_gmp_backward.argtypes = [P(LevelPlanC), P(GmpWeightsC), vp, vp, i32, vp, vp, P(GmpWeightsC),
+    lib.bsms_gmp_saved_bytes.restype = sz
+    lib.bsms_gmp_saved_bytes.argtypes = [i32, i32]
+    lib.bsms_gmp_forward.argtypes = [P(LevelPlanC), P(GmpWeightsC), vp, vp, i32, vp, vp, vp, i32, i32, i32, vp, sz, vp]
+    lib.bsms_gmp_backward.argtypes = [P(LevelPlanC), P(GmpWeightsC), vp, vp, i32, vp, vp, vp, P(GmpWeightsC),
                                       i32, i32, i32, vp, sz, vp]
     lib.bsms_launch_count.restype = i64
     lib.bsms_launch_count.argtypes = []

@@ -286,37 +286,46 @@ static int fp32_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, co
   return BSMS_OK;
 }
 
-static Fp32Acts carve(Arena& ar, long long Rn, long long Re, bool keep, bool edge_bufs = true) {
+// Node-level tensors (PsPd, aggr, node-MLP activations) live in `saved` when the caller provides it
+// (forward keeps them for backward: 3.5 KB per node row, ~9 % of the edge rows), else in the arena.
+static Fp32Acts carve(Arena& ar, long long Rn, long long Re, bool keep, bool edge_bufs, float* saved) {
   Fp32Acts a;
   long long re = Re > 0 ? Re : 1;
-  a.PsPd = ar.take<float>(Rn * 256);
+  Arena sv(saved, saved ? (size_t)-1 : 0);
+  Arena& nd = saved ? sv : ar;
+  a.PsPd = nd.take<float>(Rn * 256);
+  a.aggr = nd.take<float>(Rn * D);
+  a.N1 = nd.take<float>(Rn * D);
+  if (keep || saved) {
+    a.N2 = nd.take<float>(Rn * D);
+    a.N3 = nd.take<float>(Rn * D);
+    a.Yn = nd.take<float>(Rn * D);
+  } else {
+    a.N2 = a.N3 = a.Yn = a.N1;  // in place: a CTA owns whole rows (BN = N = 128)
+  }
   if (!edge_bufs) {
     a.A0 = a.A1 = a.A2 = a.Y = nullptr;  // the fused tcgen05 kernels keep every per-edge tensor on chip
   } else {
     a.A0 = ar.take<float>(re * D);
-  }
-  if (!edge_bufs) {
-  } else if (keep) {
-    a.A1 = ar.take<float>(re * D);
-    a.A2 = ar.take<float>(re * D);
-    a.Y = ar.take<float>(re * D);
-  } else {
-    a.A1 = a.A2 = a.Y = a.A0;  // in place: a CTA owns whole rows (BN = N = 128)
-  }
-  a.aggr = ar.take<float>(Rn * D);
-  a.N1 = ar.take<float>(Rn * D);
-  if (keep) {
-    a.N2 = ar.take<float>(Rn * D);
-    a.N3 = ar.take<float>(Rn * D);
-    a.Yn = ar.take<float>(Rn * D);
-  } else {
-    a.N2 = a.N3 = a.Yn = a.N1;
+    if (keep) {
+      a.A1 = ar.take<float>(re * D);
+      a.A2 = ar.take<float>(re * D);
+      a.Y = ar.take<float>(re * D);
+    } else {
+      a.A1 = a.A2 = a.Y = a.A0;
+    }
   }
   return a;
 }
 }  // namespace bsms
 
 using namespace bsms;
+
+extern "C" size_t bsms_gmp_saved_bytes(int32_t B, int32_t N) {
+  size_t Rn = (size_t)B * N;
+  auto f = [](size_t n) { return align_up(n * sizeof(float), 256); };
+  return f(Rn * 256) + 5 * f(Rn * D) + 256;
+}
 
 extern "C" size_t bsms_gmp_workspace_bytes(int32_t B, int32_t N, int32_t E, int32_t mode, int32_t backward) {
   (void)mode;
@@ -342,8 +351,8 @@ static int check_common(const bsms_level_plan* pl, const bsms_gmp_weights* w, co
 }
 
 extern "C" int bsms_gmp_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos,
-                                int32_t pos_batched, const float* skip, float* out, int32_t B, int32_t P, int32_t mode,
-                                void* ws, size_t ws_bytes, void* stream) {
+                                int32_t pos_batched, const float* skip, float* out, float* saved, int32_t B, int32_t P,
+                                int32_t mode, void* ws, size_t ws_bytes, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   BSMS_TRY(check_common(pl, w, x, pos, B, P, mode));
   BSMS_CHECK_ARG(out && ws, "bsms_gmp_forward: null argument");
@@ -353,7 +362,7 @@ extern "C" int bsms_gmp_forward(const bsms_level_plan* pl, const bsms_gmp_weight
   }
   const long long Rn = (long long)B * pl->n_nodes, Re = (long long)B * pl->n_edges;
   Arena ar(ws, ws_bytes);
-  Fp32Acts a = carve(ar, Rn, Re, false);
+  Fp32Acts a = carve(ar, Rn, Re, false, mode == BSMS_MODE_FP32, saved);
   uint8_t* wpack = ar.take<uint8_t>(edge_chain_pack_bytes(BSMS_MODE_FP16X3));
   BSMS_TRY(fp32_forward(pl, w, x, pos, pos_batched, B, P, a, st, mode, wpack));
   {
@@ -365,8 +374,9 @@ extern "C" int bsms_gmp_forward(const bsms_level_plan* pl, const bsms_gmp_weight
 }
 
 extern "C" int bsms_gmp_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos,
-                                 int32_t pos_batched, const float* g_out, float* g_x, const bsms_gmp_grads* gr,
-                                 int32_t B, int32_t P, int32_t mode, void* ws, size_t ws_bytes, void* stream) {
+                                 int32_t pos_batched, const float* saved, const float* g_out, float* g_x,
+                                 const bsms_gmp_grads* gr, int32_t B, int32_t P, int32_t mode, void* ws, size_t ws_bytes,
+                                 void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   BSMS_TRY(check_common(pl, w, x, pos, B, P, mode));
   BSMS_CHECK_ARG(g_out && g_x && gr && ws, "bsms_gmp_backward: null argument");
@@ -381,7 +391,9 @@ extern "C" int bsms_gmp_backward(const bsms_level_plan* pl, const bsms_gmp_weigh
   const int ldw1 = 2 * D + P + 1;
   Arena ar(ws, ws_bytes);
   const bool fused = (mode == BSMS_MODE_BF16);  // fused tcgen05 edge backward; the split modes use the fp32 path
-  Fp32Acts a = carve(ar, Rn, Re, true, !fused);
+  // with `saved` from forward the fused path recomputes nothing at node level
+  const bool have_saved = fused && saved != nullptr;
+  Fp32Acts a = carve(ar, Rn, Re, true, !fused, have_saved ? const_cast<float*>(saved) : nullptr);
   float* Ge1 = fused ? nullptr : ar.take<float>((Re > 0 ? Re : 1) * D);
   float* Ge2 = fused ? nullptr : ar.take<float>((Re > 0 ? Re : 1) * D);
   uint8_t* wpack = ar.take<uint8_t>(edge_chain_pack_bytes(BSMS_MODE_FP16X3));
@@ -390,7 +402,8 @@ extern "C" int bsms_gmp_backward(const bsms_level_plan* pl, const bsms_gmp_weigh
   float* gcat = ar.take<float>(Rn * 256);
   float* gPsPd = ar.take<float>(Rn * 256);
   // ---- recompute forward, keeping every (node-level) activation
-  BSMS_TRY(fp32_forward(pl, w, x, pos, pos_batched, B, P, a, st, fused ? BSMS_MODE_BF16 : BSMS_MODE_FP32, wpack));
+  if (!have_saved)
+    BSMS_TRY(fp32_forward(pl, w, x, pos, pos_batched, B, P, a, st, fused ? BSMS_MODE_BF16 : BSMS_MODE_FP32, wpack));
   // ---- node MLP backward
   {
     ProfScope ps_(PK_LN_BWD, st);

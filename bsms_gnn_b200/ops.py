@@ -89,9 +89,14 @@ class _GMPFunction(torch.autograd.Function):
         nbytes = int(lib.bsms_gmp_workspace_bytes(B, N, level.n_edges, mode, 0))
         ws = _lib.workspace(nbytes, x3.device)
         w = _weights_struct(params)
+        # node-level intermediates kept for backward (fused tcgen05 modes; nothing per-edge is kept)
+        saved = None
+        if mode == _lib.MODE_BF16 and any(ctx.needs_input_grad):
+            saved = torch.empty(int(lib.bsms_gmp_saved_bytes(B, N)), dtype=torch.uint8, device=x3.device)
         with torch.cuda.device(x3.device):
             check(lib.bsms_gmp_forward(level.byref(), C.byref(w), ptr(x3), ptr(pos), pos_batched, ptr(skip3), ptr(out),
-                                       B, P, mode, ptr(ws), ws.numel(), stream_ptr()))
+                                       ptr(saved), B, P, mode, ptr(ws), ws.numel(), stream_ptr()))
+        ctx.saved_nodes = saved
         ctx.save_for_backward(x3, pos, *params)
         ctx.level, ctx.mode, ctx.P, ctx.has_skip = level, mode, P, skip3 is not None
         return out
@@ -109,8 +114,9 @@ class _GMPFunction(torch.autograd.Function):
         w, gw = _weights_struct(params), _weights_struct(grads)
         with torch.cuda.device(x3.device):
             check(lib.bsms_gmp_backward(level.byref(), C.byref(w), ptr(x3), ptr(pos), 1 if pos.dim() == 3 else 0,
-                                        ptr(g_out), ptr(g_x), C.byref(gw), B, P, mode, ptr(ws), ws.numel(),
-                                        stream_ptr()))
+                                        ptr(ctx.saved_nodes), ptr(g_out), ptr(g_x), C.byref(gw), B, P, mode, ptr(ws),
+                                        ws.numel(), stream_ptr()))
+        ctx.saved_nodes = None
         return (g_x, None, g_out if ctx.has_skip else None, None, None, None, *grads)
 
 

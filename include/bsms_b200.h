@@ -141,17 +141,23 @@ typedef struct bsms_gmp_grads { /* accumulated into (+=); all required in backwa
 /* bytes of scratch bsms_gmp_forward / bsms_gmp_backward need for this problem size */
 size_t bsms_gmp_workspace_bytes(int32_t B, int32_t n_nodes, int32_t n_edges, int32_t mode,
                                 int32_t backward);
+/* `saved` (may be NULL): bsms_gmp_saved_bytes(B, n_nodes) bytes that receive the node-level
+ * intermediates (projected rows, aggregated messages, node-MLP activations; no per-edge tensor)
+ * so that backward does not recompute them. */
+size_t bsms_gmp_saved_bytes(int32_t B, int32_t n_nodes);
 int bsms_gmp_forward(const bsms_level_plan* plan, const bsms_gmp_weights* w, const float* x,
                      const float* pos, int32_t pos_batched, const float* skip /* may be NULL */,
-                     float* out, int32_t B, int32_t P, int32_t mode, void* workspace,
-                     size_t workspace_bytes, void* stream);
+                     float* out, float* saved /* may be NULL */, int32_t B, int32_t P, int32_t mode,
+                     void* workspace, size_t workspace_bytes, void* stream);
 /* Backward of the block above by recomputation (nothing is saved by forward): given g_out
  * [B,N,128] writes g_x [B,N,128] (gradient w.r.t. x INCLUDING the residual path; the gradient
  * w.r.t. skip is g_out itself) and accumulates the 16 parameter gradients.  No gradient flows to
  * pos (it is an input, src/ops/BSMS.py:75 runs under the same autograd but pos never requires
  * grad in the reference's use). */
 int bsms_gmp_backward(const bsms_level_plan* plan, const bsms_gmp_weights* w, const float* x,
-                      const float* pos, int32_t pos_batched, const float* g_out, float* g_x,
+                      const float* pos, int32_t pos_batched,
+                      const float* saved /* from forward with the same inputs, or NULL to recompute */,
+                      const float* g_out, float* g_x,
                       const bsms_gmp_grads* grads, int32_t B, int32_t P, int32_t mode,
                       void* workspace, size_t workspace_bytes, void* stream);
 
