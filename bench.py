@@ -193,7 +193,8 @@ def main():
     pos_host = (torch.from_numpy(pos).unsqueeze(0) + 0.01 * torch.randn(B, pos.shape[0], 2, generator=gen)).pin_memory()
     h_dev = h_host.to(dev).requires_grad_(True)
     pos_dev = pos_host.to(dev)
-    flat = torch.empty(sum(p.numel() for p in params), device=dev) if world > 1 else None
+    from bsms_gnn_b200.dist import GradBucket
+    bucket = GradBucket(params) if world > 1 else None
 
     def step(h, p):
         for q in params:
@@ -203,8 +204,7 @@ def main():
         loss = out.square().mean()
         loss.backward()
         if world > 1:  # data-parallel exchange: one all-reduce of the 2.15 M parameter gradients
-            torch._foreach_copy_(list(flat.split([q.numel() for q in params])), [q.grad.view(-1) for q in params])
-            dist.all_reduce(flat)
+            bucket.step_sync()
         return loss
 
     def barrier():

@@ -17,8 +17,8 @@ __host__ __device__ inline uint32_t wblk_offset(int n, int k) {
 }
 
 struct PackList {
-  const float* w[8];
-  int ld[8];
+  const float* w[12];
+  int ld[12];
   int n;
 };
 

@@ -288,7 +288,7 @@ size_t edge_chain_pack_bytes(int mode) { return (size_t)3 * (mode == BSMS_MODE_F
 // Packs W2..W4 and runs the fused edge stage.  aggr must be zero-filled by the caller.
 int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* PsPd, const float* pos,
                        int pos_batched, int B, int P, int mode, uint8_t* wpack, float* aggr, float* dbg, int dbg_stage,
-                       cudaStream_t st) {
+                       cudaStream_t st, bool prepacked) {
   const long long rows = (long long)B * pl->n_edges;
   if (rows == 0) return BSMS_OK;
   PackList pk;
@@ -320,7 +320,7 @@ int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, con
   BSMS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = std::min(sms, ceil_div(p.ntiles, 2));
   if (mode == BSMS_MODE_BF16) {
-    {
+    if (!prepacked) {
       ProfScope ps_(PK_OTHER, st);
       k_pack_weights<1><<<3, 256, 0, st>>>(pk, wpack);
       BSMS_LAUNCHED();
@@ -332,7 +332,7 @@ int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, con
     kern<<<grid, 256, smem, st>>>(p);
     BSMS_LAUNCHED();
   } else {
-    {
+    if (!prepacked) {
       ProfScope ps_(PK_OTHER, st);
       k_pack_weights<2><<<3, 256, 0, st>>>(pk, wpack);
       BSMS_LAUNCHED();

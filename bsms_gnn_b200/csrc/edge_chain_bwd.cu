@@ -394,7 +394,7 @@ size_t edge_chain_bwd_smem() { return 1024 + 6 * kWBlk + 512 * 4 + 128 * 16 * 2 
 // Fused bf16 backward of the edge stage.  gPsPd must be zero-filled; gW/gb/gW1 are accumulated into.
 int edge_chain_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const bsms_gmp_grads* gr, const float* PsPd,
                         const float* pos, int pos_batched, int B, int P, uint8_t* wpack, const float* g_aggr, int ld_g,
-                        float* gPsPd, cudaStream_t st) {
+                        float* gPsPd, cudaStream_t st, bool prepacked) {
   const long long rows = (long long)B * pl->n_edges;
   if (rows == 0) return BSMS_OK;
   PackList pk;
@@ -429,7 +429,7 @@ int edge_chain_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, co
   int dev = 0, sms = 148;
   BSMS_CUDA(cudaGetDevice(&dev));
   BSMS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  {
+  if (!prepacked) {
     ProfScope ps_(PK_OTHER, st);
     k_pack_weights<1><<<3, 256, 0, st>>>(pk, wpack);
     BSMS_LAUNCHED();

@@ -198,9 +198,27 @@ __global__ void k_add_rows(const float* __restrict__ a, const float* __restrict_
   st4(out + r * D + c, make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w));
 }
 
-struct Sizes {
-  long long Rn, Re;
-};
+int launch_ln_residual(const float* Yn, const float* x, const float* skip, float* out, long long rows, cudaStream_t st) {
+  if (rows == 0) return BSMS_OK;
+  ProfScope ps_(PK_OTHER, st);
+  k_ln_residual<<<ceil_div(rows * 32, 256), 256, 0, st>>>(Yn, x, skip, out, rows);
+  BSMS_LAUNCHED();
+  return BSMS_OK;
+}
+int launch_ln_bwd_rows(const float* Y, const float* g, int ldg, float* gY, long long rows, cudaStream_t st) {
+  if (rows == 0) return BSMS_OK;
+  ProfScope ps_(PK_LN_BWD, st);
+  k_ln_bwd<<<ceil_div(rows * 32, 256), 256, 0, st>>>(Y, g, ldg, nullptr, 0, 0, gY, rows);
+  BSMS_LAUNCHED();
+  return BSMS_OK;
+}
+int launch_add_rows(const float* a, const float* b, int ldb, float* out, long long rows, cudaStream_t st) {
+  if (rows == 0) return BSMS_OK;
+  ProfScope ps_(PK_OTHER, st);
+  k_add_rows<<<ceil_div(rows * 32, 256), 256, 0, st>>>(a, b, ldb, out, rows);
+  BSMS_LAUNCHED();
+  return BSMS_OK;
+}
 
 template <int P>
 static int edge_combine(const float* PsPd, const float* pos, int pos_batched, const bsms_level_plan* pl,
@@ -246,11 +264,18 @@ struct Fp32Acts {
 size_t edge_chain_pack_bytes(int mode);
 int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* PsPd, const float* pos,
                        int pos_batched, int B, int P, int mode, uint8_t* wpack, float* aggr, float* dbg, int dbg_stage,
-                       cudaStream_t st);
+                       cudaStream_t st, bool prepacked);
 
 int edge_chain_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const bsms_gmp_grads* gr, const float* PsPd,
                         const float* pos, int pos_batched, int B, int P, uint8_t* wpack, const float* g_aggr, int ld_g,
-                        float* gPsPd, cudaStream_t st);
+                        float* gPsPd, cudaStream_t st, bool prepacked);
+// tensor-core orchestration of a whole GMP block (gmp_tc.cu)
+int gmp_forward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos, int pos_batched,
+                   const float* skip, float* out, float* saved, int B, int P, int mode, void* ws, size_t ws_bytes,
+                   cudaStream_t st);
+int gmp_backward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos,
+                    int pos_batched, const float* saved, const float* g_out, float* g_x, const bsms_gmp_grads* gr, int B,
+                    int P, void* ws, size_t ws_bytes, cudaStream_t st);
 
 static int fp32_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos,
                         int pos_batched, int B, int P, const Fp32Acts& a, cudaStream_t st, int mode = BSMS_MODE_FP32,
@@ -265,7 +290,7 @@ static int fp32_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, co
   if (mode != BSMS_MODE_FP32) {
     // tensor-core modes: the whole edge stage is one fused kernel that reduces into aggr
     BSMS_CUDA(cudaMemsetAsync(a.aggr, 0, (size_t)Rn * D * sizeof(float), st));
-    BSMS_TRY(edge_chain_forward(pl, w, a.PsPd, pos, pos_batched, B, P, mode, wpack, a.aggr, nullptr, -1, st));
+    BSMS_TRY(edge_chain_forward(pl, w, a.PsPd, pos, pos_batched, B, P, mode, wpack, a.aggr, nullptr, -1, st, false));
   } else if (Re > 0) {
     if (P == 1) BSMS_TRY(edge_combine<1>(a.PsPd, pos, pos_batched, pl, w->w_edge[0], w->b_edge[0], a.A0, B, st));
     if (P == 2) BSMS_TRY(edge_combine<2>(a.PsPd, pos, pos_batched, pl, w->w_edge[0], w->b_edge[0], a.A0, B, st));
@@ -331,11 +356,12 @@ extern "C" size_t bsms_gmp_workspace_bytes(int32_t B, int32_t N, int32_t E, int3
   (void)mode;
   size_t Rn = (size_t)B * N, Re = (size_t)B * (E > 0 ? E : 1);
   auto f = [](size_t n) { return align_up(n * sizeof(float), 256); };
-  size_t fwd = f(Rn * 256) + f(Re * D) + 2 * f(Rn * D) + align_up(edge_chain_pack_bytes(BSMS_MODE_FP16X3), 256);
+  // covers both the fp32 layout and the tensor-core layout (node buffers + 10 packed weight blocks)
+  size_t fwd = f(Rn * 256) + f(Re * D) + 6 * f(Rn * D) + (1u << 20);
   if (!backward) return fwd + 4096;
   size_t bwd = f(Rn * 256) + 4 * f(Re * D) + 5 * f(Rn * D) + align_up(edge_chain_pack_bytes(BSMS_MODE_FP16X3), 256)
                + 2 * f(Re * D) + 2 * f(Rn * D) + 2 * f(Rn * 256);  // gradient ping-pong, gcat, gPsPd
-  return bwd + 4096;
+  return bwd + (2u << 20);
 }
 
 static int check_common(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos,
@@ -360,6 +386,8 @@ extern "C" int bsms_gmp_forward(const bsms_level_plan* pl, const bsms_gmp_weight
     set_error("bsms_gmp_forward: workspace too small");
     return BSMS_EWORKSPACE;
   }
+  if (mode != BSMS_MODE_FP32)
+    return gmp_forward_tc(pl, w, x, pos, pos_batched, skip, out, saved, B, P, mode, ws, ws_bytes, st);
   const long long Rn = (long long)B * pl->n_nodes, Re = (long long)B * pl->n_edges;
   Arena ar(ws, ws_bytes);
   Fp32Acts a = carve(ar, Rn, Re, false, mode == BSMS_MODE_FP32, saved);
@@ -386,6 +414,8 @@ extern "C" int bsms_gmp_backward(const bsms_level_plan* pl, const bsms_gmp_weigh
     set_error("bsms_gmp_backward: workspace too small");
     return BSMS_EWORKSPACE;
   }
+  if (mode == BSMS_MODE_BF16)
+    return gmp_backward_tc(pl, w, x, pos, pos_batched, saved, g_out, g_x, gr, B, P, ws, ws_bytes, st);
   const int N = pl->n_nodes, E = pl->n_edges;
   const long long Rn = (long long)B * N, Re = (long long)B * E;
   const int ldw1 = 2 * D + P + 1;
@@ -428,7 +458,7 @@ extern "C" int bsms_gmp_backward(const bsms_level_plan* pl, const bsms_gmp_weigh
   // ---- edge MLP backward (upstream of edge row e is g_aggr[dst_e] = gcat[:, 128:])
   if (Re > 0 && fused) {
     BSMS_CUDA(cudaMemsetAsync(gPsPd, 0, (size_t)Rn * 256 * sizeof(float), st));
-    BSMS_TRY(edge_chain_backward(pl, w, gr, a.PsPd, pos, pos_batched, B, P, wpack, gcat + 128, 256, gPsPd, st));
+    BSMS_TRY(edge_chain_backward(pl, w, gr, a.PsPd, pos, pos_batched, B, P, wpack, gcat + 128, 256, gPsPd, st, false));
   } else if (Re > 0) {
     {
       ProfScope ps_(PK_LN_BWD, st);
@@ -479,5 +509,5 @@ extern "C" int bsms_debug_edge_stage(const bsms_level_plan* pl, const bsms_gmp_w
   BSMS_TRY(gemm_nt(x, D, nullptr, 0, D, 0, w->w_edge[0] + (P + 1), ldw1, nullptr, nullptr, 0, PsPd, 256, Rn, D, 0, st));
   BSMS_TRY(gemm_nt(x, D, nullptr, 0, D, 0, w->w_edge[0] + (P + 1 + D), ldw1, nullptr, nullptr, 0, PsPd + 128, 256, Rn, D, 0, st));
   BSMS_CUDA(cudaMemsetAsync(aggr, 0, (size_t)Rn * D * sizeof(float), st));
-  return edge_chain_forward(pl, w, PsPd, pos, pos_batched, B, P, mode, wpack, aggr, dbg, stage, st);
+  return edge_chain_forward(pl, w, PsPd, pos, pos_batched, B, P, mode, wpack, aggr, dbg, stage, st, false);
 }

@@ -1,0 +1,174 @@
+// GMP block on the tensor-core path (BSMS_MODE_BF16 / BSMS_MODE_FP16X3): orchestration of the fused
+// edge kernels (edge_chain*.cu) and the node-level tcgen05 GEMMs (node_gemm.cu).
+// Reference: src/ops/basic.py:48-98.
+#include "chain.cuh"
+
+namespace bsms {
+
+// kernels / launchers defined in the other translation units
+int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* PsPd, const float* pos,
+                       int pos_batched, int B, int P, int mode, uint8_t* wpack, float* aggr, float* dbg, int dbg_stage,
+                       cudaStream_t st, bool prepacked);
+int edge_chain_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const bsms_gmp_grads* gr, const float* PsPd,
+                        const float* pos, int pos_batched, int B, int P, uint8_t* wpack, const float* g_aggr, int ld_g,
+                        float* gPsPd, cudaStream_t st, bool prepacked);
+size_t gmp_pack_stride(int mode);
+int gmp_pack_blocks(const PackList& pl, int mode, uint8_t* out, cudaStream_t st);
+int lin_tc(int mode, const float* X0, int ldx0, const float* X1, int ldx1, int KB, int NB, const uint8_t* const* blocks,
+           int b_mn, const float* bias, int relu, const float* mask, int ldmask, int accum, float* Y, int ldy,
+           long long rows, int kind, cudaStream_t st);
+int wgrad_tc(const float* G, int ldg, const float* X, int ldx, float* dW, int ldo, float* db, long long rows,
+             cudaStream_t st);
+int launch_ln_residual(const float* Yn, const float* x, const float* skip, float* out, long long rows, cudaStream_t st);
+int launch_ln_bwd_rows(const float* Y, const float* g, int ldg, float* gY, long long rows, cudaStream_t st);
+int launch_add_rows(const float* a, const float* b, int ldb, float* out, long long rows, cudaStream_t st);
+
+#define TC_TRY(expr)              \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != BSMS_OK) return _rc; \
+  } while (0)
+
+// packed block indices of one GMP
+enum { BW2 = 0, BW3, BW4, BW1S, BW1D, BV1A, BV1B, BV2, BV3, BV4, NBLOCKS };
+
+static int pack_all(const bsms_gmp_weights* w, int P, int mode, uint8_t* wpack, cudaStream_t st) {
+  const int ldw1 = 2 * kD + P + 1;
+  PackList pl;
+  pl.n = NBLOCKS;
+  pl.w[BW2] = w->w_edge[1]; pl.ld[BW2] = kD;
+  pl.w[BW3] = w->w_edge[2]; pl.ld[BW3] = kD;
+  pl.w[BW4] = w->w_edge[3]; pl.ld[BW4] = kD;
+  pl.w[BW1S] = w->w_edge[0] + (P + 1); pl.ld[BW1S] = ldw1;
+  pl.w[BW1D] = w->w_edge[0] + (P + 1 + kD); pl.ld[BW1D] = ldw1;
+  pl.w[BV1A] = w->w_node[0]; pl.ld[BV1A] = 2 * kD;
+  pl.w[BV1B] = w->w_node[0] + kD; pl.ld[BV1B] = 2 * kD;
+  pl.w[BV2] = w->w_node[1]; pl.ld[BV2] = kD;
+  pl.w[BV3] = w->w_node[2]; pl.ld[BV3] = kD;
+  pl.w[BV4] = w->w_node[3]; pl.ld[BV4] = kD;
+  return gmp_pack_blocks(pl, mode, wpack, st);
+}
+
+struct NodeBufs {
+  float *PsPd, *aggr, *N1, *N2, *N3, *Yn;
+};
+// same layout as gmp.cu's carve() so `saved` is interchangeable between the paths
+static NodeBufs carve_nodes(Arena& a, long long Rn) {
+  NodeBufs n;
+  n.PsPd = a.take<float>(Rn * 256);
+  n.aggr = a.take<float>(Rn * kD);
+  n.N1 = a.take<float>(Rn * kD);
+  n.N2 = a.take<float>(Rn * kD);
+  n.N3 = a.take<float>(Rn * kD);
+  n.Yn = a.take<float>(Rn * kD);
+  return n;
+}
+
+static int forward_nodes(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos,
+                         int pos_batched, int B, int P, int mode, const NodeBufs& n, uint8_t* wpack, cudaStream_t st) {
+  const long long Rn = (long long)B * pl->n_nodes;
+  const size_t bs = gmp_pack_stride(mode);
+  auto blk = [&](int i) { return (const uint8_t*)(wpack + (size_t)i * bs); };
+  {
+    const uint8_t* b[2] = {blk(BW1S), blk(BW1D)};  // Ps | Pd = x [W1s ; W1d]^T
+    TC_TRY(lin_tc(mode, x, kD, nullptr, 0, 1, 2, b, 0, nullptr, 0, nullptr, 0, 0, n.PsPd, 256, Rn, PK_NODE_FWD_GEMM, st));
+  }
+  BSMS_CUDA(cudaMemsetAsync(n.aggr, 0, (size_t)Rn * kD * sizeof(float), st));
+  TC_TRY(edge_chain_forward(pl, w, n.PsPd, pos, pos_batched, B, P, mode, wpack, n.aggr, nullptr, -1, st, true));
+  {
+    const uint8_t* b[2] = {blk(BV1A), blk(BV1B)};  // N1 = relu([x | aggr] V1^T + c1)
+    TC_TRY(lin_tc(mode, x, kD, n.aggr, kD, 2, 1, b, 0, w->b_node[0], 1, nullptr, 0, 0, n.N1, kD, Rn, PK_NODE_FWD_GEMM, st));
+  }
+  {
+    const uint8_t* b[1] = {blk(BV2)};
+    TC_TRY(lin_tc(mode, n.N1, kD, nullptr, 0, 1, 1, b, 0, w->b_node[1], 1, nullptr, 0, 0, n.N2, kD, Rn, PK_NODE_FWD_GEMM, st));
+  }
+  {
+    const uint8_t* b[1] = {blk(BV3)};
+    TC_TRY(lin_tc(mode, n.N2, kD, nullptr, 0, 1, 1, b, 0, w->b_node[2], 1, nullptr, 0, 0, n.N3, kD, Rn, PK_NODE_FWD_GEMM, st));
+  }
+  {
+    const uint8_t* b[1] = {blk(BV4)};
+    TC_TRY(lin_tc(mode, n.N3, kD, nullptr, 0, 1, 1, b, 0, w->b_node[3], 0, nullptr, 0, 0, n.Yn, kD, Rn, PK_NODE_FWD_GEMM, st));
+  }
+  return BSMS_OK;
+}
+
+int gmp_forward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos, int pos_batched,
+                   const float* skip, float* out, float* saved, int B, int P, int mode, void* ws, size_t ws_bytes,
+                   cudaStream_t st) {
+  const long long Rn = (long long)B * pl->n_nodes;
+  Arena ar(ws, ws_bytes);
+  Arena sv(saved, (size_t)-1);
+  NodeBufs n = carve_nodes(saved ? sv : ar, Rn);
+  uint8_t* wpack = ar.take<uint8_t>(NBLOCKS * 2 * kWBlk);
+  if (!ar.ok()) {
+    set_error("bsms_gmp_forward: workspace too small for the tensor-core path");
+    return BSMS_EWORKSPACE;
+  }
+  TC_TRY(pack_all(w, P, mode, wpack, st));
+  TC_TRY(forward_nodes(pl, w, x, pos, pos_batched, B, P, mode, n, wpack, st));
+  return launch_ln_residual(n.Yn, x, skip, out, Rn, st);
+}
+
+// bf16 backward: node MLP backward on tcgen05 GEMMs, fused edge backward, node-level layer-0 gradients
+int gmp_backward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos,
+                    int pos_batched, const float* saved, const float* g_out, float* g_x, const bsms_gmp_grads* gr, int B,
+                    int P, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int mode = BSMS_MODE_BF16;
+  const long long Rn = (long long)B * pl->n_nodes, Re = (long long)B * pl->n_edges;
+  const int ldw1 = 2 * kD + P + 1;
+  Arena ar(ws, ws_bytes);
+  Arena sv(const_cast<float*>(saved), (size_t)-1);
+  NodeBufs n = carve_nodes(saved ? sv : ar, Rn);
+  float* G1 = ar.take<float>(Rn * kD);
+  float* G2 = ar.take<float>(Rn * kD);
+  float* gcat = ar.take<float>(Rn * 256);
+  float* gPsPd = ar.take<float>(Rn * 256);
+  uint8_t* wpack = ar.take<uint8_t>(NBLOCKS * 2 * kWBlk);
+  if (!ar.ok()) {
+    set_error("bsms_gmp_backward: workspace too small for the tensor-core path");
+    return BSMS_EWORKSPACE;
+  }
+  const size_t bs = gmp_pack_stride(mode);
+  auto blk = [&](int i) { return (const uint8_t*)(wpack + (size_t)i * bs); };
+  TC_TRY(pack_all(w, P, mode, wpack, st));
+  if (!saved) TC_TRY(forward_nodes(pl, w, x, pos, pos_batched, B, P, mode, n, wpack, st));
+  // ---- node MLP backward
+  TC_TRY(launch_ln_bwd_rows(n.Yn, g_out, kD, G1, Rn, st));  // gYn
+  TC_TRY(wgrad_tc(G1, kD, n.N3, kD, gr->w_node[3], kD, gr->b_node[3], Rn, st));
+  {
+    const uint8_t* b[1] = {blk(BV4)};
+    TC_TRY(lin_tc(mode, G1, kD, nullptr, 0, 1, 1, b, 1, nullptr, 0, n.N3, kD, 0, G2, kD, Rn, PK_DGRAD, st));
+  }
+  TC_TRY(wgrad_tc(G2, kD, n.N2, kD, gr->w_node[2], kD, gr->b_node[2], Rn, st));
+  {
+    const uint8_t* b[1] = {blk(BV3)};
+    TC_TRY(lin_tc(mode, G2, kD, nullptr, 0, 1, 1, b, 1, nullptr, 0, n.N2, kD, 0, G1, kD, Rn, PK_DGRAD, st));
+  }
+  TC_TRY(wgrad_tc(G1, kD, n.N1, kD, gr->w_node[1], kD, gr->b_node[1], Rn, st));
+  {
+    const uint8_t* b[1] = {blk(BV2)};
+    TC_TRY(lin_tc(mode, G1, kD, nullptr, 0, 1, 1, b, 1, nullptr, 0, n.N1, kD, 0, G2, kD, Rn, PK_DGRAD, st));
+  }
+  // layer 0 of the node MLP: input [x | aggr]
+  TC_TRY(wgrad_tc(G2, kD, x, kD, gr->w_node[0], 2 * kD, gr->b_node[0], Rn, st));
+  TC_TRY(wgrad_tc(G2, kD, n.aggr, kD, gr->w_node[0] + kD, 2 * kD, nullptr, Rn, st));
+  {
+    const uint8_t* b[2] = {blk(BV1A), blk(BV1B)};  // gcat = G2 V1 : [g_x part | g_aggr]
+    TC_TRY(lin_tc(mode, G2, kD, nullptr, 0, 1, 2, b, 1, nullptr, 0, nullptr, 0, 0, gcat, 256, Rn, PK_DGRAD, st));
+  }
+  TC_TRY(launch_add_rows(g_out, gcat, 256, g_x, Rn, st));
+  // ---- edge stage backward (fused) and the node-level gradients of the first edge layer
+  if (Re > 0) {
+    BSMS_CUDA(cudaMemsetAsync(gPsPd, 0, (size_t)Rn * 256 * sizeof(float), st));
+    TC_TRY(edge_chain_backward(pl, w, gr, n.PsPd, pos, pos_batched, B, P, wpack, gcat + 128, 256, gPsPd, st, true));
+    TC_TRY(wgrad_tc(gPsPd, 256, x, kD, gr->w_edge[0] + (P + 1), ldw1, nullptr, Rn, st));
+    TC_TRY(wgrad_tc(gPsPd + 128, 256, x, kD, gr->w_edge[0] + (P + 1 + kD), ldw1, nullptr, Rn, st));
+    const uint8_t* b[2] = {blk(BW1S), blk(BW1D)};  // g_x += gPs W1s + gPd W1d
+    TC_TRY(lin_tc(mode, gPsPd, 256, gPsPd + 128, 256, 2, 1, b, 1, nullptr, 0, nullptr, 0, 1, g_x, kD, Rn, PK_DGRAD, st));
+  }
+  return BSMS_OK;
+}
+
+}  // namespace bsms

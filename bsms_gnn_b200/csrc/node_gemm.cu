@@ -1,0 +1,372 @@
+// Node-level dense layers on tcgen05: the per-node pre-projection of the first edge layer, the
+// node MLP, and their data / weight gradients (reference: src/ops/basic.py:6-23, :97-98).
+//
+//   k_lin<NSPLIT>  Y[rows, NB*128] = epi( [X0 | X1][rows, KB*128] x W )      TS-form, thread = row = TMEM lane
+//                  - forward form : W blocks are [n][k] images read K-major
+//                  - dgrad form   : W blocks are [k][n] images read MN-major (= W^T), no transposed copy
+//                  - epilogue     : +bias, ReLU, mask by (M > 0) (ReLU backward), += Y
+//                  One warpgroup per CTA, 256 TMEM columns per CTA, two CTAs per SM ping-pong.
+//   k_wgrad_tc     dW[128,128] += G^T X over ALL rows: both fp32 row tiles are converted to bf16
+//                  canonical tiles in shared memory (double buffered) and consumed MN-major; the
+//                  accumulator stays in TMEM for the whole persistent loop; bias gradient = column sums.
+#include "chain.cuh"
+
+namespace bsms {
+
+struct LinParams {
+  const float* X[2];
+  int ldx[2];
+  int KB, NB;
+  const uint8_t* wblk[4];  // packed block of (nb, kb) at index nb*2+kb
+  int b_mn;                // 1: blocks are [k][n] images, read MN-major (dgrad form)
+  const float* bias;
+  int relu;
+  const float* mask;
+  int ldmask;
+  int accum;
+  float* Y;
+  int ldy;
+  long long rows;
+  int ntiles;
+};
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(128, 2) k_lin(const LinParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t FMT = (NSPLIT == 1) ? 1u : 0u;
+  constexpr uint32_t BLK = NSPLIT * kWBlk;
+  constexpr float OUT_SCALE = (NSPLIT == 1) ? 1.f : 1.f / (kActScale * kWScale);
+  const uint32_t idesc = make_idesc(FMT, 128, 128, 0, p.b_mn ? 1u : 0u);
+  const uint32_t s0 = smem_u32(smem_raw);
+  const uint32_t sbase = (s0 + 1023u) & ~1023u;
+  uint8_t* sp = smem_raw + (sbase - s0);
+  const int nblk = p.KB * p.NB;
+  float* s_bias = reinterpret_cast<float*>(sp + 2 * BLK);  // [256]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 256);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t bar_w = smem_u32(&s_bar[0]), bar_m = smem_u32(&s_bar[1]);
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_m, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(s_tmem), 256);
+  for (int i = tid; i < 128 * p.NB; i += 128) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+  if (tid == 0) {
+    mbar_expect_tx(bar_w, nblk * BLK);
+    for (int nb = 0; nb < p.NB; ++nb)
+      for (int kb = 0; kb < p.KB; ++kb)
+        bulk_g2s(sbase + (nb * p.KB + kb) * BLK, p.wblk[nb * 2 + kb], BLK, bar_w);
+    mbar_wait(bar_w, 0);
+  }
+  const uint32_t d_tmem = tmem_base;       // 128 columns
+  const uint32_t a_tmem = tmem_base + 128;  // 64 (hi) [+ 64 (lo)]
+  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  uint32_t phase = 0;
+
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    const long long row = (long long)tile * 128 + tid;
+    const bool valid = row < p.rows;
+    for (int nb = 0; nb < p.NB; ++nb) {
+      for (int kb = 0; kb < p.KB; ++kb) {
+        if (nb == 0 || p.KB > 1) {
+          const float* xr = p.X[kb] + row * p.ldx[kb];
+#pragma unroll 1
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            float v[32];
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4) {
+              float4 a = valid ? ld4(xr + c0 + q4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+              v[q4 * 4 + 0] = a.x; v[q4 * 4 + 1] = a.y; v[q4 * 4 + 2] = a.z; v[q4 * 4 + 3] = a.w;
+            }
+            uint32_t hi[16];
+            if (NSPLIT == 1) {
+#pragma unroll
+              for (int t = 0; t < 16; ++t) hi[t] = pack_bf16(v[2 * t], v[2 * t + 1]);
+              tmem_st16(a_tmem + lane_off + (c0 >> 1), hi);
+            } else {
+              uint32_t lo[16];
+#pragma unroll
+              for (int t = 0; t < 16; ++t) {
+                float s0_ = v[2 * t] * kActScale, s1_ = v[2 * t + 1] * kActScale;
+                __half h0 = __float2half_rn(s0_), h1 = __float2half_rn(s1_);
+                hi[t] = pack_f16(h0, h1);
+                lo[t] = pack_f16(__float2half_rn(s0_ - __half2float(h0)), __float2half_rn(s1_ - __half2float(h1)));
+              }
+              tmem_st16(a_tmem + lane_off + (c0 >> 1), hi);
+              tmem_st16(a_tmem + lane_off + 64 + (c0 >> 1), lo);
+            }
+          }
+          wait_st();
+        }
+        fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+          fence_after_sync();
+          const uint32_t wb = sbase + (nb * p.KB + kb) * BLK;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t off = p.b_mn ? ks * 2048 : (ks >> 2) * 16384 + (ks & 3) * 32;
+            const uint32_t lbo = p.b_mn ? 16384 : 16;
+            const uint64_t bhi = smem_desc_sw128(wb + off, lbo, 1024);
+            mma_ts(d_tmem, a_tmem + ks * 8, bhi, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+            if (NSPLIT == 2) {
+              const uint64_t blo = smem_desc_sw128(wb + kWBlk + off, lbo, 1024);
+              mma_ts(d_tmem, a_tmem + 64 + ks * 8, bhi, idesc, 1);
+              mma_ts(d_tmem, a_tmem + ks * 8, blo, idesc, 1);
+            }
+          }
+          mma_commit(bar_m);
+        }
+        mbar_wait(bar_m, phase);
+        phase ^= 1;
+        fence_after_sync();
+      }
+      // ---- epilogue of N block nb
+      float* yr = p.Y + row * p.ldy + nb * 128;
+      const float* mr = p.mask ? p.mask + row * p.ldmask + nb * 128 : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(d_tmem + lane_off + c0, r);
+        wait_ld();
+        if (valid) {
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x = __uint_as_float(r[q4 * 4 + e]) * OUT_SCALE + s_bias[nb * 128 + c0 + q4 * 4 + e];
+              o[e] = p.relu ? fmaxf(x, 0.f) : x;
+            }
+            if (mr) {
+              float4 m = ld4(mr + c0 + q4 * 4);
+              o[0] = m.x > 0.f ? o[0] : 0.f; o[1] = m.y > 0.f ? o[1] : 0.f;
+              o[2] = m.z > 0.f ? o[2] : 0.f; o[3] = m.w > 0.f ? o[3] : 0.f;
+            }
+            if (p.accum) {
+              float4 y = ld4(yr + c0 + q4 * 4);
+              o[0] += y.x; o[1] += y.y; o[2] += y.z; o[3] += y.w;
+            }
+            st4(yr + c0 + q4 * 4, make_float4(o[0], o[1], o[2], o[3]));
+          }
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+// ------------------------------------------------------------------------------------------
+struct WgradParams {
+  const float* G;
+  int ldg;
+  const float* X;
+  int ldx;
+  float* dW;  // [128, ldo] accumulated
+  int ldo;
+  float* db;  // [128] accumulated, may be null
+  long long rows;
+  int ntiles;
+};
+
+__device__ __forceinline__ uint32_t t_off(int r, int chunk) {
+  return (uint32_t)((chunk >> 3) * 16384 + r * 128 + (((chunk & 7) ^ (r & 7)) << 4));
+}
+
+__global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t IDESC_MM = make_idesc(1, 128, 128, 1, 1);
+  const uint32_t s0 = smem_u32(smem_raw);
+  const uint32_t sbase = (s0 + 1023u) & ~1023u;
+  uint8_t* sp = smem_raw + (sbase - s0);
+  // stage s: G tile at (2s) * 32 KB, X tile at (2s+1) * 32 KB
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(sp + 4 * kWBlk);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar0 = smem_u32(&s_bar[0]), bar1 = smem_u32(&s_bar[1]);
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar1, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(s_tmem), 128);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+  const int r = tid >> 1, h = tid & 1;  // row of the tile, channel half
+  const int cc = tid & 127, rh = tid >> 7;
+  float acc_b = 0.f;
+  uint32_t ph[2] = {0u, 0u};
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    const int s = it & 1;
+    // the MMAs that read stage s two iterations ago must be done before it is overwritten
+    if (it >= 2) {
+      mbar_wait(s ? bar1 : bar0, ph[s]);
+      ph[s] ^= 1;
+    }
+    const long long row = (long long)tile * 128 + r;
+    const bool valid = row < p.rows;
+    uint8_t* tg = sp + (2 * s) * kWBlk;
+    uint8_t* tx = sp + (2 * s + 1) * kWBlk;
+    const float* gr = p.G + row * p.ldg + 64 * h;
+    const float* xr = p.X + row * p.ldx + 64 * h;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 a0 = valid ? ld4(gr + 8 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 a1 = valid ? ld4(gr + 8 * j + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      uint4 u;
+      u.x = pack_bf16(a0.x, a0.y); u.y = pack_bf16(a0.z, a0.w); u.z = pack_bf16(a1.x, a1.y); u.w = pack_bf16(a1.z, a1.w);
+      *reinterpret_cast<uint4*>(tg + t_off(r, 8 * h + j)) = u;
+      float4 b0 = valid ? ld4(xr + 8 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 b1 = valid ? ld4(xr + 8 * j + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      u.x = pack_bf16(b0.x, b0.y); u.y = pack_bf16(b0.z, b0.w); u.z = pack_bf16(b1.x, b1.y); u.w = pack_bf16(b1.z, b1.w);
+      *reinterpret_cast<uint4*>(tx + t_off(r, 8 * h + j)) = u;
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      const uint32_t ag = sbase + (2 * s) * kWBlk, ax = sbase + (2 * s + 1) * kWBlk;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t ad = smem_desc_sw128(ag + ks * 2048, 16384, 1024);
+        const uint64_t bd = smem_desc_sw128(ax + ks * 2048, 16384, 1024);
+        mma_ss(tmem_base, ad, bd, IDESC_MM, (it > 0 || ks > 0) ? 1u : 0u);
+      }
+      mma_commit(s ? bar1 : bar0);
+    }
+    if (p.db) {  // bias gradient: column sums of the (bf16-rounded) G tile, overlapping the MMAs
+      float sacc = 0.f;
+#pragma unroll 8
+      for (int rr = rh * 64; rr < rh * 64 + 64; ++rr) {
+        const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(tg + t_off(rr, cc >> 3) + (cc & 7) * 2);
+        sacc += __bfloat162float(*e);
+      }
+      acc_b += sacc;
+    }
+  }
+  // drain: wait for the last (up to two) commits
+  const int n_it = it;
+  for (int k = (n_it >= 2 ? n_it - 2 : 0); k < n_it; ++k) {
+    const int s = k & 1;
+    mbar_wait(s ? bar1 : bar0, ph[s]);
+    ph[s] ^= 1;
+  }
+  fence_after_sync();
+  if (n_it > 0) {
+    const int q = warp & 3, hh = warp >> 2;  // TMEM lane = output channel n
+    const int n = q * 32 + lane;
+    uint32_t r0[32], r1[32];
+    const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + 64 * hh;
+    tmem_ld32(ta, r0);
+    tmem_ld32(ta + 32, r1);
+    wait_ld();
+    float* dst = p.dW + (size_t)n * p.ldo + 64 * hh;
+#pragma unroll
+    for (int t = 0; t < 32; ++t) atomicAdd(dst + t, __uint_as_float(r0[t]));
+#pragma unroll
+    for (int t = 0; t < 32; ++t) atomicAdd(dst + 32 + t, __uint_as_float(r1[t]));
+    if (p.db) atomicAdd(p.db + cc, acc_b);
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static int g_sms = 0;
+static int sm_count() {
+  if (g_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return g_sms;
+}
+
+// one launch packs every 128x128 block a GMP call needs; returns the byte stride between blocks
+size_t gmp_pack_stride(int mode) { return (size_t)(mode == BSMS_MODE_FP16X3 ? 2 : 1) * kWBlk; }
+
+int gmp_pack_blocks(const PackList& pl, int mode, uint8_t* out, cudaStream_t st) {
+  ProfScope ps_(PK_OTHER, st);
+  if (mode == BSMS_MODE_FP16X3)
+    k_pack_weights<2><<<pl.n, 256, 0, st>>>(pl, out);
+  else
+    k_pack_weights<1><<<pl.n, 256, 0, st>>>(pl, out);
+  BSMS_LAUNCHED();
+  return BSMS_OK;
+}
+
+int lin_tc(int mode, const float* X0, int ldx0, const float* X1, int ldx1, int KB, int NB, const uint8_t* const* blocks,
+           int b_mn, const float* bias, int relu, const float* mask, int ldmask, int accum, float* Y, int ldy,
+           long long rows, int kind, cudaStream_t st) {
+  if (rows == 0) return BSMS_OK;
+  LinParams p;
+  p.X[0] = X0;
+  p.X[1] = X1;
+  p.ldx[0] = ldx0;
+  p.ldx[1] = ldx1;
+  p.KB = KB;
+  p.NB = NB;
+  for (int i = 0; i < 4; ++i) p.wblk[i] = nullptr;
+  for (int nb = 0; nb < NB; ++nb)
+    for (int kb = 0; kb < KB; ++kb) p.wblk[nb * 2 + kb] = blocks[nb * KB + kb];
+  p.b_mn = b_mn;
+  p.bias = bias;
+  p.relu = relu;
+  p.mask = mask;
+  p.ldmask = ldmask;
+  p.accum = accum;
+  p.Y = Y;
+  p.ldy = ldy;
+  p.rows = rows;
+  p.ntiles = ceil_div(rows, 128);
+  const int grid = std::min(2 * sm_count(), p.ntiles);
+  ProfScope ps_(kind, st);
+  if (mode == BSMS_MODE_FP16X3) {
+    const size_t smem = 1024 + 4 * kWBlk + 1024 + 64;  // 2 blocks of 64 KB: one CTA per SM by shared memory
+    BSMS_CUDA(cudaFuncSetAttribute(k_lin<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_lin<2><<<grid, 128, smem, st>>>(p);
+  } else {
+    // 2 blocks of 32 KB; padded to 80 KB so that at most two CTAs (2 x 256 TMEM columns) share an SM
+    const size_t smem = 80 * 1024;
+    BSMS_CUDA(cudaFuncSetAttribute(k_lin<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_lin<1><<<grid, 128, smem, st>>>(p);
+  }
+  BSMS_LAUNCHED();
+  return BSMS_OK;
+}
+
+int wgrad_tc(const float* G, int ldg, const float* X, int ldx, float* dW, int ldo, float* db, long long rows,
+             cudaStream_t st) {
+  if (rows == 0) return BSMS_OK;
+  WgradParams p;
+  p.G = G;
+  p.ldg = ldg;
+  p.X = X;
+  p.ldx = ldx;
+  p.dW = dW;
+  p.ldo = ldo;
+  p.db = db;
+  p.rows = rows;
+  p.ntiles = ceil_div(rows, 128);
+  const size_t smem = 1024 + 4 * kWBlk + 64;
+  BSMS_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope ps_(PK_WGRAD, st);
+  k_wgrad_tc<<<std::min(sm_count(), p.ntiles), 256, smem, st>>>(p);
+  BSMS_LAUNCHED();
+  return BSMS_OK;
+}
+
+}  // namespace bsms

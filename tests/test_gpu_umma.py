@@ -98,32 +98,41 @@ def test_bsgmp_forward_tensor_modes(mode, tol):
 
 
 def gmp_bf16_emulated(x, g, pos, p, prefix):
-    """fp64 GMP whose edge layers 1..3 see bf16-rounded operands (activations and weights), with a
-    straight-through gradient — the arithmetic of BSMS_MODE_BF16's fused edge kernels (the first edge
-    layer and the node MLP stay fp32 in that mode).  Test infrastructure only."""
+    """fp64 GMP in which every tensor-core GEMM sees bf16-rounded operands (activations and weights)
+    with a straight-through gradient — the arithmetic of BSMS_MODE_BF16: the per-node projections
+    Ps = x W1s^T, Pd = x W1d^T, edge layers 1..3 and all four node-MLP layers; the fiber term, biases,
+    ReLU, LayerNorm and all sums stay fp32/fp64.  Test infrastructure only."""
     def rb(t):
         return t + (t.detach().float().bfloat16().double() - t.detach())
+    lin = torch.nn.functional.linear
+    P = pos.shape[-1]
     i, j = g[0], g[1]
-    xi, xj = x[..., i, :], x[..., j, :]
+    W1, b1 = p[f"{prefix}.mlp_edge.seq.0.weight"], p[f"{prefix}.mlp_edge.seq.0.bias"]
+    ps = lin(rb(x), rb(W1[:, P + 1:P + 1 + 128]))
+    pd = lin(rb(x), rb(W1[:, P + 1 + 128:]))
     pp = pos if pos.dim() == 3 else pos.unsqueeze(0).expand(x.shape[0], -1, -1)
     dd = pp[..., i, :] - pp[..., j, :]
     fiber = torch.cat([dd, dd.norm(dim=-1, keepdim=True)], -1)
-    lin = torch.nn.functional.linear
-    h = torch.relu(lin(torch.cat([fiber, xi, xj], -1), p[f"{prefix}.mlp_edge.seq.0.weight"], p[f"{prefix}.mlp_edge.seq.0.bias"]))
+    h = torch.relu(ps[..., i, :] + pd[..., j, :] + b1 + lin(fiber, W1[:, :P + 1]))
     for l in (2, 4):
         h = torch.relu(lin(rb(h), rb(p[f"{prefix}.mlp_edge.seq.{l}.weight"]), p[f"{prefix}.mlp_edge.seq.{l}.bias"]))
     y = lin(rb(h), rb(p[f"{prefix}.mlp_edge.seq.6.weight"]), p[f"{prefix}.mlp_edge.seq.6.bias"])
     mu = y.mean(-1, keepdim=True)
     e = (y - mu) / torch.sqrt(((y - mu) ** 2).mean(-1, keepdim=True) + 1e-5)
     aggr = O.scatter_sum(e, j, -2, x.shape[-2])
-    return O.mlp(torch.cat([x, aggr], -1), p, f"{prefix}.mlp_node", 3) + x
+    n = torch.cat([x, aggr], -1)
+    for l in (0, 2, 4):
+        n = torch.relu(lin(rb(n), rb(p[f"{prefix}.mlp_node.seq.{l}.weight"]), p[f"{prefix}.mlp_node.seq.{l}.bias"]))
+    yn = lin(rb(n), rb(p[f"{prefix}.mlp_node.seq.6.weight"]), p[f"{prefix}.mlp_node.seq.6.bias"])
+    mu = yn.mean(-1, keepdim=True)
+    return (yn - mu) / torch.sqrt(((yn - mu) ** 2).mean(-1, keepdim=True) + 1e-5) + x
 
 
 @pytest.mark.parametrize("hname,level,B,P,pos_batched", [("grid12", 0, 1, 2, False), ("ico3", 1, 2, 3, True),
                                                          ("grid44", 0, 2, 2, False), ("grid72", 5, 3, 2, True)])
 def test_gmp_backward_bf16_fused(hname, level, B, P, pos_batched):
     """Fused tcgen05 backward (bf16 operands) against an fp64 evaluation with the SAME rounding points
-    in the forward (bf16 operands of edge layers 1..3).  Tolerance 2e-2 in the L2-relative norm per
+    in the forward (bf16 operands of every tensor-core GEMM).  Tolerance 2e-2 in the L2-relative norm per
     tensor: what is left is the bf16 rounding of the gradient tiles inside the backward GEMMs (2^-9
     per operand) plus a handful of ReLU-mask flips where a pre-activation sits within 1e-4 of zero
     (max-rel is reported too but a single flipped unit moves it by percents on the small meshes).
@@ -160,6 +169,6 @@ def test_gmp_backward_bf16_fused(hname, level, B, P, pos_batched):
     print(f"\n[bf16 bwd {hname} L{level} B{B}] L2-rel " + " ".join(
         f"{k.replace('mlp_', '').replace('.seq', '')}={v:.1e}" for k, v in errs.items()) +
         f" | worst max-rel {max(mx.values()):.1e}")
-    assert errs["out"] < 2e-4
+    assert errs["out"] < 1e-3
     for k, v in errs.items():
         assert v < 2e-2, (k, v)
