@@ -250,11 +250,13 @@ def main():
 
     # ---- roofline pass: per-kernel CUDA-event timing inside the library (rank 0)
     roofline, breakdown, roofline_edge = None, None, None
+    prof_steps = 2
     if rank == 0:
         _lib.prof_enable(True)
-        prof_steps = 2
-        for _ in range(prof_steps):
-            step(h_dev, pos_dev)
+    for _ in range(prof_steps):  # every rank runs the steps (the all-reduce inside is collective)
+        step(h_dev, pos_dev)
+    barrier()
+    if rank == 0:
         prof = _lib.prof_collect()
         _lib.prof_enable(False)
         pk = peaks()
