@@ -1,29 +1,34 @@
-// Fused GMP edge stage on tcgen05 (sm_100a):  gather Ps[src]+Pd[dst] (+fiber, +b1) -> ReLU ->
+// Fused GMP edge stage on tcgen05 (sm_100a):  gather Ps[src]+Pd[dst] (+fiber) -> ReLU ->
 // 3 x (128x128x128 UMMA + bias [+ReLU]) -> LayerNorm -> segmented sum over dst-sorted rows ->
 // red.add into aggr.  No per-edge tensor ever reaches HBM.   (reference: src/ops/basic.py:66-94)
 //
 // CTA = 256 threads = 2 warpgroups; each warpgroup owns one 128-edge tile at a time (thread = edge
-// row = TMEM lane) with a private TMEM region [D 128 cols | A_hi 64 | A_lo 64], so the two tiles
-// ping-pong: one warpgroup's CUDA-core epilogue overlaps the other's MMAs.  Activations never
-// leave TMEM between layers (tcgen05.ld -> bias/ReLU/convert in registers -> tcgen05.st as the
-// next A operand, TS-form MMA); the three weight matrices are staged ONCE per CTA into shared
-// memory by cp.async.bulk (pre-packed in the 128B-swizzled K-major UMMA layout) and stay resident
-// for the whole persistent loop.
+// row = TMEM lane) with a private TMEM region [D 128 cols | A_hi 64 | A_lo 64 / ones], so the two
+// tiles ping-pong: one warpgroup's CUDA-core epilogue overlaps the other's MMAs.  Activations never
+// leave TMEM between layers (tcgen05.ld -> ReLU/convert in registers -> tcgen05.st as the next A
+// operand, TS-form MMA); the three weight matrices are staged ONCE per CTA into shared memory by
+// cp.async.bulk (pre-packed in the 128B-swizzled K-major UMMA layout) and stay resident for the
+// whole persistent loop.
 //
-// NSPLIT = 1: bf16 operands (BSMS_MODE_BF16).  NSPLIT = 2: fp16 hi/lo split of both operands, 3 MMAs
-// per K step into one fp32 accumulator (BSMS_MODE_FP16X3): x ~ hi + lo with 22 significant bits, the
-// dropped lo*lo term is 2^-22 relative — the fp32-parity mode.  Operands are pre-scaled by exact
-// powers of two (activations 2^4, weights 2^8) so the lo parts stay in fp16's normal range; the
-// accumulator is rescaled by 2^-12 in the epilogue.
-#include "common.cuh"
-#include "umma.cuh"
+// NSPLIT = 1: bf16 operands (BSMS_MODE_BF16).  The biases ride in the MMA: a constant "ones" A
+// operand (K = 16, first column 1) times a [bias | 0] B block initialises the accumulator, so the
+// epilogues are a bare ReLU + convert.
+// NSPLIT = 2: fp16 hi/lo split of both operands, 3 MMAs per K step into one fp32 accumulator
+// (BSMS_MODE_FP16X3): x ~ hi + lo with 22 significant bits, the dropped lo*lo term is 2^-22 relative —
+// the fp32-parity mode.  Operands are pre-scaled by exact powers of two (activations 2^4, weights
+// 2^8) so the lo parts stay in fp16's normal range; the accumulator is rescaled by 2^-12 and the
+// fp32 bias added in the epilogue.
+//
+// PsPd holds the per-node projections with b1 already folded into the Pd half.
 #include "chain.cuh"
 
 namespace bsms {
 using namespace umma;
 
+constexpr uint32_t kBiasBlk = 128 * 128;  // [bias | 0] B block for one K=16 step: 128 rows x 128 B
+
 struct EdgeChainParams {
-  const float* PsPd;  // [B*N, 256]
+  const float* PsPd;  // [B*N, 256], b1 folded into the Pd half
   const float* pos;
   int pos_batched, P;
   const int32_t* src_d;
@@ -31,6 +36,7 @@ struct EdgeChainParams {
   const float* W1;  // mlp_edge layer 0 weight [128, 2*128+P+1] (fiber columns are read from it)
   const float* b[4];
   const uint8_t* wpack;  // [3][NSPLIT] packed blocks
+  const uint8_t* bpack;  // [3] packed bias blocks (bf16 mode)
   float* aggr;           // [B*N, 128], zero-initialised
   int B, N, E;
   long long rows;
@@ -38,6 +44,16 @@ struct EdgeChainParams {
   float* dbg;
   int dbg_stage;
 };
+
+// b2..b4 -> three 16 KB blocks in the K-major SW128 image: element (n, k=0) = bias[n], rest 0
+__global__ void k_pack_bias(const float* b2, const float* b3, const float* b4, uint8_t* __restrict__ out) {
+  const float* b = blockIdx.x == 0 ? b2 : (blockIdx.x == 1 ? b3 : b4);
+  uint8_t* o = out + (size_t)blockIdx.x * kBiasBlk;
+  for (int i = threadIdx.x; i < (int)kBiasBlk / 16; i += blockDim.x) reinterpret_cast<uint4*>(o)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  for (int n = threadIdx.x; n < 128; n += blockDim.x)
+    *reinterpret_cast<__nv_bfloat16*>(o + wblk_offset(n, 0)) = __float2bfloat16_rn(b[n]);
+}
 
 template <int NSPLIT>
 __device__ __forceinline__ void store_act32(uint32_t a_tmem, int c0, const float (&v)[32]) {
@@ -66,18 +82,20 @@ template <int NSPLIT, int CH>
 __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int NW = 3 * NSPLIT;
+  constexpr bool BIAS_MMA = (NSPLIT == 1);
   constexpr uint32_t FMT = (NSPLIT == 1) ? 1u : 0u;  // bf16 : f16
   constexpr uint32_t IDESC = make_idesc(FMT, 128, 128);
   constexpr float OUT_SCALE = (NSPLIT == 1) ? 1.f : 1.f / (kActScale * kWScale);
-  constexpr int G = 32 / CH;        // row groups per warp in the segmented reduce
-  constexpr int RPG = 32 / G;       // rows per group
+  constexpr int G = 32 / CH;   // row groups per warp in the segmented reduce
+  constexpr int RPG = 32 / G;  // rows per group
   const uint32_t s0 = smem_u32(smem_raw);
   const uint32_t sbase = (s0 + 1023u) & ~1023u;
   uint8_t* sp = smem_raw + (sbase - s0);
-  uint8_t* s_w = sp;
-  float* s_bias = reinterpret_cast<float*>(sp + NW * kWBlk);  // [4][128]
-  float4* s_F = reinterpret_cast<float4*>(s_bias + 512);      // [128]
-  float* s_stage = reinterpret_cast<float*>(s_F + 128);       // [8][32][CH+1]
+  const uint32_t bias_blk = sbase + NW * kWBlk;                       // 3 x 16 KB (bf16 mode only)
+  uint8_t* sp2 = sp + NW * kWBlk + (BIAS_MMA ? 3 * kBiasBlk : 0);
+  float* s_bias = reinterpret_cast<float*>(sp2);         // [3][128]: b2, b3, b4 (fp16x3 mode)
+  float4* s_F = reinterpret_cast<float4*>(s_bias + 384);  // [128]
+  float* s_stage = reinterpret_cast<float*>(s_F + 128);   // [8][32][CH+1]
   int* s_tgt = reinterpret_cast<int*>(s_stage + 8 * 32 * (CH + 1));
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tgt + 256);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 3);
@@ -94,7 +112,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
-  for (int i = tid; i < 512; i += 256) s_bias[i] = p.b[i >> 7][i & 127];
+  for (int i = tid; i < 384; i += 256) s_bias[i] = p.b[1 + (i >> 7)][i & 127];
   {
     const int ldw1 = 2 * kD + p.P + 1;
     for (int c = tid; c < 128; c += 256) {
@@ -108,12 +126,22 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
   fence_after_sync();
   const uint32_t tmem_base = *s_tmem;
   if (tid == 0) {
-    mbar_expect_tx(bar_w, NW * kWBlk);
+    mbar_expect_tx(bar_w, NW * kWBlk + (BIAS_MMA ? 3 * kBiasBlk : 0));
     for (int blk = 0; blk < NW; ++blk) bulk_g2s(sbase + blk * kWBlk, p.wpack + (size_t)blk * kWBlk, kWBlk, bar_w);
+    if (BIAS_MMA)
+      for (int l = 0; l < 3; ++l) bulk_g2s(bias_blk + l * kBiasBlk, p.bpack + (size_t)l * kBiasBlk, kBiasBlk, bar_w);
   }
   const uint32_t d_tmem = tmem_base + wg * 256;
   const uint32_t a_tmem = d_tmem + 128;
+  const uint32_t ones_tmem = d_tmem + 192;  // bf16 mode: 16 columns, element k=0 is 1.0
   const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+  if (BIAS_MMA) {
+    uint32_t ones[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) ones[t] = 0u;
+    ones[0] = 0x00003F80u;  // bf16 pair (1.0, 0.0)
+    tmem_st16(ones_tmem + lane_off, ones);
+  }
   uint32_t phase = 0;
   bool weights_ready = false;
   float* stage = s_stage + warp * 32 * (CH + 1);
@@ -129,8 +157,14 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
       i = p.src_d[e];
       j = p.dst_d[e];
     }
-    tgt[lane] = valid ? b * p.N + j : -1;
-    // ---- prologue: fiber, gather-add, ReLU -> A
+    const int my_tgt = valid ? b * p.N + j : -1;
+    __syncwarp();
+    tgt[lane] = my_tgt;
+    // run starts of the dst-sorted rows of this warp (bit rr set: row rr starts a new destination)
+    const int prev_tgt = __shfl_up_sync(0xffffffffu, my_tgt, 1);
+    const uint32_t startmask = __ballot_sync(0xffffffffu, lane == 0 || my_tgt != prev_tgt);
+    // ---- prologue: fiber, gather-add, ReLU -> A   (loads of the next 32 channels are in flight
+    //      while the current 32 are combined)
     float fib[4] = {0.f, 0.f, 0.f, 0.f};
     if (valid) {
       const float* pb = p.pos + (p.pos_batched ? (size_t)b * p.N * p.P : 0);
@@ -144,20 +178,33 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
     }
     const float* ps_row = p.PsPd + ((size_t)b * p.N + i) * 256;
     const float* pd_row = p.PsPd + ((size_t)b * p.N + j) * 256 + 128;
-#pragma unroll 1
+    float4 ga[8], gd[8];
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q4 = 0; q4 < 8; ++q4) {
+      ga[q4] = valid ? ld4(ps_row + q4 * 4) : z4;
+      gd[q4] = valid ? ld4(pd_row + q4 * 4) : z4;
+    }
+#pragma unroll
     for (int c0 = 0; c0 < 128; c0 += 32) {
       float v[32];
 #pragma unroll
       for (int q4 = 0; q4 < 8; ++q4) {
-        float4 a = valid ? ld4(ps_row + c0 + q4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 d = valid ? ld4(pd_row + c0 + q4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        v[q4 * 4 + 0] = a.x + d.x; v[q4 * 4 + 1] = a.y + d.y; v[q4 * 4 + 2] = a.z + d.z; v[q4 * 4 + 3] = a.w + d.w;
+        v[q4 * 4 + 0] = ga[q4].x + gd[q4].x; v[q4 * 4 + 1] = ga[q4].y + gd[q4].y;
+        v[q4 * 4 + 2] = ga[q4].z + gd[q4].z; v[q4 * 4 + 3] = ga[q4].w + gd[q4].w;
+      }
+      if (c0 + 32 < 128) {
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          ga[q4] = valid ? ld4(ps_row + c0 + 32 + q4 * 4) : z4;
+          gd[q4] = valid ? ld4(pd_row + c0 + 32 + q4 * 4) : z4;
+        }
       }
 #pragma unroll
       for (int t = 0; t < 32; ++t) {
         float4 f = s_F[c0 + t];
-        float x = v[t] + s_bias[c0 + t] + f.x * fib[0] + f.y * fib[1] + f.z * fib[2] + f.w * fib[3];
-        v[t] = valid ? fmaxf(x, 0.f) : 0.f;
+        float x = v[t] + f.x * fib[0] + f.y * fib[1] + f.z * fib[2] + f.w * fib[3];
+        v[t] = fmaxf(x, 0.f);
       }
       if (p.dbg && p.dbg_stage == 0 && valid) {
 #pragma unroll
@@ -178,11 +225,13 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
         }
         fence_after_sync();
         const uint32_t wb = sbase + layer * NSPLIT * kWBlk;
+        if (BIAS_MMA)  // D = ones x [bias | 0]^T
+          mma_ts(d_tmem, ones_tmem, smem_desc_sw128(bias_blk + layer * kBiasBlk, 16, 1024), IDESC, 0);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
           const uint32_t koff = (ks >> 2) * 16384 + (ks & 3) * 32;
           const uint64_t bhi = smem_desc_sw128(wb + koff, 16, 1024);
-          mma_ts(d_tmem, a_tmem + ks * 8, bhi, IDESC, ks > 0);
+          mma_ts(d_tmem, a_tmem + ks * 8, bhi, IDESC, (BIAS_MMA || ks > 0) ? 1u : 0u);
           if (NSPLIT == 2) {
             const uint64_t blo = smem_desc_sw128(wb + kWBlk + koff, 16, 1024);
             mma_ts(d_tmem, a_tmem + 64 + ks * 8, bhi, IDESC, 1);
@@ -194,7 +243,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
       mbar_wait(bar_m, phase);
       phase ^= 1;
       fence_after_sync();
-      const float* bias = s_bias + (layer + 1) * 128;
+      const float* bias = s_bias + layer * 128;
       if (layer < 2) {
 #pragma unroll 1
         for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -203,7 +252,10 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
           wait_ld();
           float v[32];
 #pragma unroll
-          for (int t = 0; t < 32; ++t) v[t] = fmaxf(__uint_as_float(r[t]) * OUT_SCALE + bias[c0 + t], 0.f);
+          for (int t = 0; t < 32; ++t) {
+            const float x = BIAS_MMA ? __uint_as_float(r[t]) : fmaf(__uint_as_float(r[t]), OUT_SCALE, bias[c0 + t]);
+            v[t] = fmaxf(x, 0.f);
+          }
           if (p.dbg && p.dbg_stage == layer + 1 && valid) {
 #pragma unroll
             for (int t = 0; t < 32; ++t) p.dbg[row * 128 + c0 + t] = v[t];
@@ -211,30 +263,29 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
           store_act32<NSPLIT>(a_tmem + lane_off, c0, v);
         }
       } else {
-        // ---- final: LayerNorm over the row (two passes over TMEM), then segmented reduce by dst
-        float sum = 0.f;
+        // ---- final: LayerNorm over the row.  Pass 1: shifted sums (shift = first element, so the
+        //      one-pass variance has no cancellation); pass 2: normalise + segmented reduce by dst.
+        float shift = 0.f, sum = 0.f, ssq = 0.f;
 #pragma unroll 1
         for (int c0 = 0; c0 < 128; c0 += 32) {
           uint32_t r[32];
           tmem_ld32(d_tmem + lane_off + c0, r);
           wait_ld();
-#pragma unroll
-          for (int t = 0; t < 32; ++t) sum += __uint_as_float(r[t]) * OUT_SCALE + bias[c0 + t];
-        }
-        const float mean = sum * (1.f / 128.f);
-        float ssq = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(d_tmem + lane_off + c0, r);
-          wait_ld();
+          if (c0 == 0) shift = BIAS_MMA ? __uint_as_float(r[0]) : fmaf(__uint_as_float(r[0]), OUT_SCALE, bias[0]);
 #pragma unroll
           for (int t = 0; t < 32; ++t) {
-            float dlt = __uint_as_float(r[t]) * OUT_SCALE + bias[c0 + t] - mean;
-            ssq += dlt * dlt;
+            const float y = BIAS_MMA ? __uint_as_float(r[t]) : fmaf(__uint_as_float(r[t]), OUT_SCALE, bias[c0 + t]);
+            const float dlt = y - shift;
+            sum += dlt;
+            ssq = fmaf(dlt, dlt, ssq);
           }
         }
-        const float rstd = 1.f / sqrtf(ssq * (1.f / 128.f) + 1e-5f);
+        const float mean_d = sum * (1.f / 128.f);
+        const float var = fmaxf(ssq * (1.f / 128.f) - mean_d * mean_d, 0.f);
+        const float rstd = 1.f / sqrtf(var + 1e-5f);
+        const float mean = shift + mean_d;
+        const int ch = lane % CH, grp = lane / CH;
+        const uint32_t gm = (startmask >> (grp * RPG)) | 1u;
 #pragma unroll 1
         for (int c0 = 0; c0 < 128; c0 += 32) {
           uint32_t r[32];
@@ -242,30 +293,37 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
           wait_ld();
           if (p.dbg && p.dbg_stage == 3 && valid) {
 #pragma unroll
-            for (int t = 0; t < 32; ++t) p.dbg[row * 128 + c0 + t] = __uint_as_float(r[t]) * OUT_SCALE + bias[c0 + t];
+            for (int t = 0; t < 32; ++t)
+              p.dbg[row * 128 + c0 + t] = BIAS_MMA ? __uint_as_float(r[t]) : fmaf(__uint_as_float(r[t]), OUT_SCALE, bias[c0 + t]);
           }
 #pragma unroll
           for (int sub = 0; sub < 32; sub += CH) {
             __syncwarp();
 #pragma unroll
-            for (int t = 0; t < CH; ++t)
-              stage[lane * (CH + 1) + t] = (__uint_as_float(r[sub + t]) * OUT_SCALE + bias[c0 + sub + t] - mean) * rstd;
-            __syncwarp();
-            // lanes switch to channel ownership: ch = lane % CH, row group = lane / CH
-            const int ch = lane % CH, grp = lane / CH;
-            float acc = 0.f;
-            int cur = -1;
-            for (int rr = grp * RPG; rr < (grp + 1) * RPG; ++rr) {
-              int t_ = tgt[rr];
-              float m = stage[rr * (CH + 1) + ch];
-              if (t_ != cur) {
-                if (cur >= 0) atomicAdd(p.aggr + (size_t)cur * 128 + c0 + sub + ch, acc);
-                cur = t_;
-                acc = 0.f;
-              }
-              acc += m;
+            for (int t = 0; t < CH; ++t) {
+              const float y = BIAS_MMA ? __uint_as_float(r[sub + t])
+                                       : fmaf(__uint_as_float(r[sub + t]), OUT_SCALE, bias[c0 + sub + t]);
+              stage[lane * (CH + 1) + t] = (y - mean) * rstd;
             }
-            if (cur >= 0) atomicAdd(p.aggr + (size_t)cur * 128 + c0 + sub + ch, acc);
+            __syncwarp();
+            // lanes own channels now and walk the rows of their group; a set bit in gm starts a new
+            // destination: flush the finished run with one red.add per channel (128 B per warp)
+            float* dstc = p.aggr + c0 + sub + ch;
+            const float* col = stage + (grp * RPG) * (CH + 1) + ch;
+            float acc = col[0];
+            int cur = tgt[grp * RPG];
+#pragma unroll
+            for (int rl = 1; rl < RPG; ++rl) {
+              const float m = col[rl * (CH + 1)];
+              if ((gm >> rl) & 1u) {
+                if (cur >= 0) atomicAdd(dstc + (size_t)cur * 128, acc);
+                cur = tgt[grp * RPG + rl];
+                acc = m;
+              } else {
+                acc += m;
+              }
+            }
+            if (cur >= 0) atomicAdd(dstc + (size_t)cur * 128, acc);
           }
         }
         __syncwarp();
@@ -280,15 +338,17 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
 
 template <int NSPLIT, int CH>
 static size_t edge_chain_smem() {
-  return 1024 + 3 * NSPLIT * kWBlk + 512 * 4 + 128 * 16 + 8 * 32 * (CH + 1) * 4 + 256 * 4 + 3 * 8 + 16;
+  return 1024 + 3 * NSPLIT * kWBlk + (NSPLIT == 1 ? 3 * kBiasBlk : 0) + 384 * 4 + 128 * 16 + 8 * 32 * (CH + 1) * 4 +
+         256 * 4 + 3 * 8 + 16;
 }
 
-size_t edge_chain_pack_bytes(int mode) { return (size_t)3 * (mode == BSMS_MODE_FP16X3 ? 2 : 1) * kWBlk; }
+size_t edge_chain_pack_bytes(int mode) { return (size_t)3 * (mode == BSMS_MODE_FP16X3 ? 2 : 1) * kWBlk + 3 * kBiasBlk; }
 
-// Packs W2..W4 and runs the fused edge stage.  aggr must be zero-filled by the caller.
+// Runs the fused edge stage.  aggr must be zero-filled by the caller; PsPd carries b1 in its Pd half.
+// wpack: [3][NSPLIT] weight blocks followed (at wpack + bias_off) by the three bias blocks (bf16).
 int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* PsPd, const float* pos,
                        int pos_batched, int B, int P, int mode, uint8_t* wpack, float* aggr, float* dbg, int dbg_stage,
-                       cudaStream_t st, bool prepacked) {
+                       cudaStream_t st, bool prepacked, uint8_t* bpack) {
   const long long rows = (long long)B * pl->n_edges;
   if (rows == 0) return BSMS_OK;
   PackList pk;
@@ -307,6 +367,7 @@ int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, con
   p.W1 = w->w_edge[0];
   for (int l = 0; l < 4; ++l) p.b[l] = w->b_edge[l];
   p.wpack = wpack;
+  p.bpack = bpack;
   p.aggr = aggr;
   p.B = B;
   p.N = pl->n_nodes;
@@ -323,6 +384,11 @@ int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, con
     if (!prepacked) {
       ProfScope ps_(PK_OTHER, st);
       k_pack_weights<1><<<3, 256, 0, st>>>(pk, wpack);
+      BSMS_LAUNCHED();
+    }
+    {
+      ProfScope ps_(PK_OTHER, st);
+      k_pack_bias<<<3, 128, 0, st>>>(w->b_edge[1], w->b_edge[2], w->b_edge[3], bpack);
       BSMS_LAUNCHED();
     }
     auto kern = k_edge_chain<1, 32>;

@@ -23,7 +23,7 @@
 namespace bsms {
 
 struct EdgeBwdParams {
-  const float* PsPd;  // [B*N, 256]
+  const float* PsPd;  // [B*N, 256], b1 folded into the Pd half
   const float* pos;
   int pos_batched, P;
   const int32_t* src_d;
@@ -104,7 +104,11 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
-  for (int i = tid; i < 512; i += 256) s_bias[i] = p.b[i >> 7][i & 127];
+  // b2..b4 are rounded to bf16 exactly as the forward kernel sees them (they ride in its MMA)
+  for (int i = tid; i < 512; i += 256) {
+    const float bv = p.b[i >> 7][i & 127];
+    s_bias[i] = i < 128 ? bv : __bfloat162float(__float2bfloat16_rn(bv));
+  }
   {
     const int ldw1 = 2 * kD + p.P + 1;
     for (int c = tid; c < 128; c += 256) {
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       for (int t = 0; t < 64; ++t) {
         const int c = 64 * h + t;
         float4 f = s_F[c];
-        float x = v[t] + s_bias[c] + f.x * fib[0] + f.y * fib[1] + f.z * fib[2] + f.w * fib[3];
+        float x = v[t] + f.x * fib[0] + f.y * fib[1] + f.z * fib[2] + f.w * fib[3];
         const bool on = valid && x > 0.f;
         v[t] = on ? x : 0.f;
         mask[t >> 5] |= (on ? 1u : 0u) << (t & 31);

@@ -264,7 +264,7 @@ struct Fp32Acts {
 size_t edge_chain_pack_bytes(int mode);
 int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* PsPd, const float* pos,
                        int pos_batched, int B, int P, int mode, uint8_t* wpack, float* aggr, float* dbg, int dbg_stage,
-                       cudaStream_t st, bool prepacked);
+                       cudaStream_t st, bool prepacked, uint8_t* bpack);
 
 int edge_chain_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const bsms_gmp_grads* gr, const float* PsPd,
                         const float* pos, int pos_batched, int B, int P, uint8_t* wpack, const float* g_aggr, int ld_g,
@@ -289,8 +289,8 @@ static int fp32_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, co
                    D, 0, st, PK_NODE_FWD_GEMM));
   if (mode != BSMS_MODE_FP32) {
     // tensor-core modes: the whole edge stage is one fused kernel that reduces into aggr
-    BSMS_CUDA(cudaMemsetAsync(a.aggr, 0, (size_t)Rn * D * sizeof(float), st));
-    BSMS_TRY(edge_chain_forward(pl, w, a.PsPd, pos, pos_batched, B, P, mode, wpack, a.aggr, nullptr, -1, st, false));
+    set_error("internal: tensor-core modes are orchestrated by gmp_tc.cu");
+    return BSMS_EINVAL;
   } else if (Re > 0) {
     if (P == 1) BSMS_TRY(edge_combine<1>(a.PsPd, pos, pos_batched, pl, w->w_edge[0], w->b_edge[0], a.A0, B, st));
     if (P == 2) BSMS_TRY(edge_combine<2>(a.PsPd, pos, pos_batched, pl, w->w_edge[0], w->b_edge[0], a.A0, B, st));
@@ -507,7 +507,9 @@ extern "C" int bsms_debug_edge_stage(const bsms_level_plan* pl, const bsms_gmp_w
   uint8_t* wpack = ar.take<uint8_t>(edge_chain_pack_bytes(BSMS_MODE_FP16X3));
   BSMS_CHECK_ARG(ar.ok(), "bsms_debug_edge_stage: workspace too small");
   BSMS_TRY(gemm_nt(x, D, nullptr, 0, D, 0, w->w_edge[0] + (P + 1), ldw1, nullptr, nullptr, 0, PsPd, 256, Rn, D, 0, st));
-  BSMS_TRY(gemm_nt(x, D, nullptr, 0, D, 0, w->w_edge[0] + (P + 1 + D), ldw1, nullptr, nullptr, 0, PsPd + 128, 256, Rn, D, 0, st));
+  // the fused kernels expect b1 folded into the Pd half
+  BSMS_TRY(gemm_nt(x, D, nullptr, 0, D, 0, w->w_edge[0] + (P + 1 + D), ldw1, w->b_edge[0], nullptr, 0, PsPd + 128, 256, Rn, D, 0, st));
   BSMS_CUDA(cudaMemsetAsync(aggr, 0, (size_t)Rn * D * sizeof(float), st));
-  return edge_chain_forward(pl, w, PsPd, pos, pos_batched, B, P, mode, wpack, aggr, dbg, stage, st, false);
+  return edge_chain_forward(pl, w, PsPd, pos, pos_batched, B, P, mode, wpack, aggr, dbg, stage, st, false,
+                            wpack + 6 * 32768);
 }

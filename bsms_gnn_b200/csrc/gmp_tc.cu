@@ -8,7 +8,7 @@ namespace bsms {
 // kernels / launchers defined in the other translation units
 int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* PsPd, const float* pos,
                        int pos_batched, int B, int P, int mode, uint8_t* wpack, float* aggr, float* dbg, int dbg_stage,
-                       cudaStream_t st, bool prepacked);
+                       cudaStream_t st, bool prepacked, uint8_t* bpack);
 int edge_chain_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const bsms_gmp_grads* gr, const float* PsPd,
                         const float* pos, int pos_batched, int B, int P, uint8_t* wpack, const float* g_aggr, int ld_g,
                         float* gPsPd, cudaStream_t st, bool prepacked);
@@ -32,7 +32,24 @@ int launch_add_rows(const float* a, const float* b, int ldb, float* out, long lo
 // packed block indices of one GMP
 enum { BW2 = 0, BW3, BW4, BW1S, BW1D, BV1A, BV1B, BV2, BV3, BV4, NBLOCKS };
 
+// bias of the fused projection GEMM: [0 (Ps half) | b1 (Pd half)] — b1 rides with Pd into the edge kernels
+__global__ void k_bias_sd(const float* __restrict__ b1, float* __restrict__ out) {
+  const int i = threadIdx.x;
+  out[i] = i < 128 ? 0.f : b1[i - 128];
+}
+
+// scratch layout behind the packed weight blocks
+constexpr size_t kPackBytes = (size_t)10 * 2 * kWBlk;   // NBLOCKS blocks, hi+lo
+constexpr size_t kBiasPackOff = kPackBytes;             // three 16 KB bias blocks of the edge chain
+constexpr size_t kBiasSdOff = kPackBytes + 3 * 16384;   // 256 floats
+constexpr size_t kScratchBytes = kBiasSdOff + 1024;
+
 static int pack_all(const bsms_gmp_weights* w, int P, int mode, uint8_t* wpack, cudaStream_t st) {
+  {
+    ProfScope ps_(PK_OTHER, st);
+    k_bias_sd<<<1, 256, 0, st>>>(w->b_edge[0], reinterpret_cast<float*>(wpack + kBiasSdOff));
+    BSMS_LAUNCHED();
+  }
   const int ldw1 = 2 * kD + P + 1;
   PackList pl;
   pl.n = NBLOCKS;
@@ -71,10 +88,12 @@ static int forward_nodes(const bsms_level_plan* pl, const bsms_gmp_weights* w, c
   auto blk = [&](int i) { return (const uint8_t*)(wpack + (size_t)i * bs); };
   {
     const uint8_t* b[2] = {blk(BW1S), blk(BW1D)};  // Ps | Pd = x [W1s ; W1d]^T
-    TC_TRY(lin_tc(mode, x, kD, nullptr, 0, 1, 2, b, 0, nullptr, 0, nullptr, 0, 0, n.PsPd, 256, Rn, PK_NODE_FWD_GEMM, st));
+    TC_TRY(lin_tc(mode, x, kD, nullptr, 0, 1, 2, b, 0, reinterpret_cast<const float*>(wpack + kBiasSdOff), 0, nullptr, 0, 0,
+                  n.PsPd, 256, Rn, PK_NODE_FWD_GEMM, st));
   }
   BSMS_CUDA(cudaMemsetAsync(n.aggr, 0, (size_t)Rn * kD * sizeof(float), st));
-  TC_TRY(edge_chain_forward(pl, w, n.PsPd, pos, pos_batched, B, P, mode, wpack, n.aggr, nullptr, -1, st, true));
+  TC_TRY(edge_chain_forward(pl, w, n.PsPd, pos, pos_batched, B, P, mode, wpack, n.aggr, nullptr, -1, st, true,
+                            wpack + kBiasPackOff));
   {
     const uint8_t* b[2] = {blk(BV1A), blk(BV1B)};  // N1 = relu([x | aggr] V1^T + c1)
     TC_TRY(lin_tc(mode, x, kD, n.aggr, kD, 2, 1, b, 0, w->b_node[0], 1, nullptr, 0, 0, n.N1, kD, Rn, PK_NODE_FWD_GEMM, st));
@@ -101,7 +120,7 @@ int gmp_forward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const f
   Arena ar(ws, ws_bytes);
   Arena sv(saved, (size_t)-1);
   NodeBufs n = carve_nodes(saved ? sv : ar, Rn);
-  uint8_t* wpack = ar.take<uint8_t>(NBLOCKS * 2 * kWBlk);
+  uint8_t* wpack = ar.take<uint8_t>(kScratchBytes);
   if (!ar.ok()) {
     set_error("bsms_gmp_forward: workspace too small for the tensor-core path");
     return BSMS_EWORKSPACE;
@@ -125,7 +144,7 @@ int gmp_backward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const 
   float* G2 = ar.take<float>(Rn * kD);
   float* gcat = ar.take<float>(Rn * 256);
   float* gPsPd = ar.take<float>(Rn * 256);
-  uint8_t* wpack = ar.take<uint8_t>(NBLOCKS * 2 * kWBlk);
+  uint8_t* wpack = ar.take<uint8_t>(kScratchBytes);
   if (!ar.ok()) {
     set_error("bsms_gmp_backward: workspace too small for the tensor-core path");
     return BSMS_EWORKSPACE;

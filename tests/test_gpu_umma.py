@@ -115,8 +115,8 @@ def gmp_bf16_emulated(x, g, pos, p, prefix):
     fiber = torch.cat([dd, dd.norm(dim=-1, keepdim=True)], -1)
     h = torch.relu(ps[..., i, :] + pd[..., j, :] + b1 + lin(fiber, W1[:, :P + 1]))
     for l in (2, 4):
-        h = torch.relu(lin(rb(h), rb(p[f"{prefix}.mlp_edge.seq.{l}.weight"]), p[f"{prefix}.mlp_edge.seq.{l}.bias"]))
-    y = lin(rb(h), rb(p[f"{prefix}.mlp_edge.seq.6.weight"]), p[f"{prefix}.mlp_edge.seq.6.bias"])
+        h = torch.relu(lin(rb(h), rb(p[f"{prefix}.mlp_edge.seq.{l}.weight"]), rb(p[f"{prefix}.mlp_edge.seq.{l}.bias"])))
+    y = lin(rb(h), rb(p[f"{prefix}.mlp_edge.seq.6.weight"]), rb(p[f"{prefix}.mlp_edge.seq.6.bias"]))  # biases ride in the MMA
     mu = y.mean(-1, keepdim=True)
     e = (y - mu) / torch.sqrt(((y - mu) ** 2).mean(-1, keepdim=True) + 1e-5)
     aggr = O.scatter_sum(e, j, -2, x.shape[-2])
