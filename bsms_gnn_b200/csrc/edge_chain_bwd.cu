@@ -202,47 +202,72 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     uint32_t m0[2] = {0u, 0u}, m1[2] = {0u, 0u}, m2[2] = {0u, 0u};
 
     // a0 (gather) -> dst tile; returns the ReLU mask
+    // 32 fp32 values -> bf16 -> chunks [chunk0, chunk0+4) of row r
+    auto store32 = [&](uint8_t* tile, int chunk0, const float (&v)[32]) {
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        uint4 u;
+        u.x = pack_bf16(v[8 * jj + 0], v[8 * jj + 1]); u.y = pack_bf16(v[8 * jj + 2], v[8 * jj + 3]);
+        u.z = pack_bf16(v[8 * jj + 4], v[8 * jj + 5]); u.w = pack_bf16(v[8 * jj + 6], v[8 * jj + 7]);
+        *reinterpret_cast<uint4*>(tile + tile_off(r, chunk0 + jj)) = u;
+      }
+    };
+    // every phase handles this thread's 64 channels as two halves of 32 (register budget)
     auto gather_a0 = [&](uint8_t* dst_tile, uint32_t (&mask)[2]) {
-      float v[64];
 #pragma unroll
-      for (int q4 = 0; q4 < 16; ++q4) {
-        float4 a = valid ? ld4(ps_row + q4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 d = valid ? ld4(pd_row + q4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        v[q4 * 4 + 0] = a.x + d.x; v[q4 * 4 + 1] = a.y + d.y; v[q4 * 4 + 2] = a.z + d.z; v[q4 * 4 + 3] = a.w + d.w;
-      }
-      mask[0] = mask[1] = 0u;
+      for (int hh = 0; hh < 2; ++hh) {
+        float v[32];
 #pragma unroll
-      for (int t = 0; t < 64; ++t) {
-        const int c = 64 * h + t;
-        float4 f = s_F[c];
-        float x = v[t] + f.x * fib[0] + f.y * fib[1] + f.z * fib[2] + f.w * fib[3];
-        const bool on = valid && x > 0.f;
-        v[t] = on ? x : 0.f;
-        mask[t >> 5] |= (on ? 1u : 0u) << (t & 31);
+        for (int q4 = 0; q4 < 8; ++q4) {
+          float4 a = valid ? ld4(ps_row + 32 * hh + q4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 d = valid ? ld4(pd_row + 32 * hh + q4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[q4 * 4 + 0] = a.x + d.x; v[q4 * 4 + 1] = a.y + d.y; v[q4 * 4 + 2] = a.z + d.z; v[q4 * 4 + 3] = a.w + d.w;
+        }
+        uint32_t mk = 0u;
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          float4 f = s_F[64 * h + 32 * hh + t];
+          float x = v[t] + f.x * fib[0] + f.y * fib[1] + f.z * fib[2] + f.w * fib[3];
+          const bool on = valid && x > 0.f;
+          v[t] = on ? x : 0.f;
+          mk |= (on ? 1u : 0u) << t;
+        }
+        mask[hh] = mk;
+        store32(dst_tile, 8 * h + 4 * hh, v);
       }
-      store_tile64(dst_tile, r, h, v);
     };
     // activation epilogue: D + bias -> ReLU -> tile, mask
     auto act_epilogue = [&](const float* bias, uint8_t* dst_tile, uint32_t (&mask)[2]) {
-      float v[64];
-      load_d64(d_mine, v);
-      mask[0] = mask[1] = 0u;
 #pragma unroll
-      for (int t = 0; t < 64; ++t) {
-        float x = v[t] + bias[64 * h + t];
-        const bool on = x > 0.f;
-        v[t] = on ? x : 0.f;
-        mask[t >> 5] |= (on ? 1u : 0u) << (t & 31);
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t rr_[32];
+        tmem_ld32(d_mine + 32 * hh, rr_);
+        wait_ld();
+        float v[32];
+        uint32_t mk = 0u;
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          float x = __uint_as_float(rr_[t]) + bias[64 * h + 32 * hh + t];
+          const bool on = x > 0.f;
+          v[t] = on ? x : 0.f;
+          mk |= (on ? 1u : 0u) << t;
+        }
+        mask[hh] = mk;
+        store32(dst_tile, 8 * h + 4 * hh, v);
       }
-      store_tile64(dst_tile, r, h, v);
     };
     // gradient epilogue: D . mask -> tile
     auto grad_epilogue = [&](const uint32_t (&mask)[2], uint8_t* dst_tile) {
-      float v[64];
-      load_d64(d_mine, v);
 #pragma unroll
-      for (int t = 0; t < 64; ++t) v[t] = ((mask[t >> 5] >> (t & 31)) & 1u) ? v[t] : 0.f;
-      store_tile64(dst_tile, r, h, v);
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t rr_[32];
+        tmem_ld32(d_mine + 32 * hh, rr_);
+        wait_ld();
+        float v[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) v[t] = ((mask[hh] >> t) & 1u) ? __uint_as_float(rr_[t]) : 0.f;
+        store32(dst_tile, 8 * h + 4 * hh, v);
+      }
     };
 
     // ---- recompute the forward chain
@@ -266,25 +291,34 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       issue_gemm(aT[2], aW[2], false);
       mma_commit(bar_m);
     }
-    wait_mma();
-    // ---- LayerNorm backward: gy = rstd * (g - mean(g) - yhat * mean(g * yhat)) -> T0
+    // upstream gradient row g_aggr[dst] (this thread's 64 channels): issued before the MMA wait
+    float g[64];
     {
-      float y[64], g[64];
-      load_d64(d_mine, y);
       const float* grow = p.g_aggr + ((size_t)b * p.N + j) * p.ld_g + 64 * h;
-      float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
 #pragma unroll
       for (int q4 = 0; q4 < 16; ++q4) {
         float4 gv = valid ? ld4(grow + q4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         g[q4 * 4 + 0] = gv.x; g[q4 * 4 + 1] = gv.y; g[q4 * 4 + 2] = gv.z; g[q4 * 4 + 3] = gv.w;
       }
+    }
+    wait_mma();
+    // ---- LayerNorm backward: gy = rstd * (g - mean(g) - yhat * mean(g * yhat)) -> T0
+    //      two sweeps over this thread's 64 accumulator columns, 32 at a time (register budget)
+    {
+      float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
 #pragma unroll
-      for (int t = 0; t < 64; ++t) {
-        y[t] += s_bias[384 + 64 * h + t];
-        s1 += y[t];
-        s2 += y[t] * y[t];
-        s3 += g[t];
-        s4 += g[t] * y[t];
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t rr_[32];
+        tmem_ld32(d_mine + 32 * hh, rr_);
+        wait_ld();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const float yv = __uint_as_float(rr_[t]) + s_bias[384 + 64 * h + 32 * hh + t];
+          s1 += yv;
+          s2 = fmaf(yv, yv, s2);
+          s3 += g[32 * hh + t];
+          s4 = fmaf(g[32 * hh + t], yv, s4);
+        }
       }
       s_x[h * 128 + r] = make_float4(s1, s2, s3, s4);
       __syncthreads();
@@ -296,11 +330,25 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       const float c1 = s3 * (1.f / 128.f);
       const float c2 = rstd * (s4 - mean * s3) * (1.f / 128.f);
 #pragma unroll
-      for (int t = 0; t < 64; ++t) {
-        const float yh = (y[t] - mean) * rstd;
-        y[t] = valid ? rstd * (g[t] - c1 - yh * c2) : 0.f;
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t rr_[32];
+        tmem_ld32(d_mine + 32 * hh, rr_);
+        wait_ld();
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          float o8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int t = 8 * jj + e;
+            const float yh = (__uint_as_float(rr_[t]) + s_bias[384 + 64 * h + 32 * hh + t] - mean) * rstd;
+            o8[e] = valid ? rstd * (g[32 * hh + t] - c1 - yh * c2) : 0.f;
+          }
+          uint4 u;
+          u.x = pack_bf16(o8[0], o8[1]); u.y = pack_bf16(o8[2], o8[3]);
+          u.z = pack_bf16(o8[4], o8[5]); u.w = pack_bf16(o8[6], o8[7]);
+          *reinterpret_cast<uint4*>(s_T[0] + tile_off(r, 8 * h + 4 * hh + jj)) = u;
+        }
       }
-      store_tile64(s_T[0], r, h, y);
     }
     sync_all();
     if (tid == 0) {
@@ -335,20 +383,25 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     wait_mma();
     // ---- g0 = D . m0 : scatter to the projected-row gradients, stage in T2 for gb1 / gF
     {
-      float v[64];
-      load_d64(d_mine, v);
+      float* gs = p.gPsPd + ((size_t)b * p.N + i) * 256 + 64 * h;
+      float* gd = p.gPsPd + ((size_t)b * p.N + j) * 256 + 128 + 64 * h;
 #pragma unroll
-      for (int t = 0; t < 64; ++t) v[t] = ((m0[t >> 5] >> (t & 31)) & 1u) ? v[t] : 0.f;
-      if (valid) {
-        float* gs = p.gPsPd + ((size_t)b * p.N + i) * 256 + 64 * h;
-        float* gd = p.gPsPd + ((size_t)b * p.N + j) * 256 + 128 + 64 * h;
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t rr_[32];
+        tmem_ld32(d_mine + 32 * hh, rr_);
+        wait_ld();
+        float v[32];
 #pragma unroll
-        for (int q4 = 0; q4 < 16; ++q4) {
-          red_add_v4(gs + q4 * 4, v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
-          red_add_v4(gd + q4 * 4, v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
+        for (int t = 0; t < 32; ++t) v[t] = ((m0[hh] >> t) & 1u) ? __uint_as_float(rr_[t]) : 0.f;
+        if (valid) {
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            red_add_v4(gs + 32 * hh + q4 * 4, v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
+            red_add_v4(gd + 32 * hh + q4 * 4, v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
+          }
         }
+        store32(s_T[2], 8 * h + 4 * hh, v);
       }
-      store_tile64(s_T[2], r, h, v);
     }
     __syncthreads();
     {
