@@ -59,6 +59,10 @@ k_conv128(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr, c
   if (gw >= (long long)B * n_out) return;
   int b = (int)(gw / n_out), r = (int)(gw - (long long)b * n_out);
   int node = rowmap ? rowmap[r] : r;
+  if (node < 0) {  // output row without a source row (partitioned runs: coarse ghost whose fine node is remote)
+    st4(out + ((size_t)b * n_out + r) * 128 + lane * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+    return;
+  }
   int k0 = rowptr[node], k1 = rowptr[node + 1];
   const float* xb = x + (size_t)b * n_in * 128 + lane * 4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -112,7 +116,8 @@ __global__ void k_conv_any(const int32_t* __restrict__ rowptr, const int32_t* __
   int node = rowmap ? rowmap[r] : r;
   const float* xb = x + (size_t)b * n_in * C + c;
   float acc = 0.f;
-  for (int k = rowptr[node]; k < rowptr[node + 1]; ++k) {
+  const int kbeg = node < 0 ? 0 : rowptr[node], kend = node < 0 ? 0 : rowptr[node + 1];
+  for (int k = kbeg; k < kend; ++k) {
     int j = nbr[k];
     if (nbrmap) j = nbrmap[j];
     if (j >= 0) acc += ew[k] * xb[(size_t)j * C];
@@ -182,9 +187,10 @@ extern "C" int bsms_cal_ew(const bsms_level_plan* p, const float* w, float* ew_o
 extern "C" int bsms_permute_ew(const bsms_level_plan* p, const float* ew_orig, float* ew_d, float* ew_s,
                                void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  BSMS_CHECK_ARG(p && ew_orig && ew_d && ew_s, "bsms_permute_ew: null argument");
+  BSMS_CHECK_ARG(p != nullptr, "bsms_permute_ew: null plan");
   int E = p->n_edges;
   if (E == 0) return BSMS_OK;
+  BSMS_CHECK_ARG(ew_orig && ew_d && ew_s, "bsms_permute_ew: null argument");
   k_ew_from_orig<<<ceil_div(E, 256), 256, 0, st>>>(ew_orig, p->perm_d, E, ew_d);
   BSMS_LAUNCHED();
   k_ew_to_s<<<ceil_div(E, 256), 256, 0, st>>>(ew_d, p->s2d, E, ew_s);
