@@ -353,15 +353,19 @@ extern "C" size_t bsms_gmp_saved_bytes(int32_t B, int32_t N) {
 }
 
 extern "C" size_t bsms_gmp_workspace_bytes(int32_t B, int32_t N, int32_t E, int32_t mode, int32_t backward) {
-  (void)mode;
   size_t Rn = (size_t)B * N, Re = (size_t)B * (E > 0 ? E : 1);
   auto f = [](size_t n) { return align_up(n * sizeof(float), 256); };
-  // covers both the fp32 layout and the tensor-core layout (node buffers + 10 packed weight blocks)
-  size_t fwd = f(Rn * 256) + f(Re * D) + 6 * f(Rn * D) + (1u << 20);
-  if (!backward) return fwd + 4096;
-  size_t bwd = f(Rn * 256) + 4 * f(Re * D) + 5 * f(Rn * D) + align_up(edge_chain_pack_bytes(BSMS_MODE_FP16X3), 256)
-               + 2 * f(Re * D) + 2 * f(Rn * D) + 2 * f(Rn * 256);  // gradient ping-pong, gcat, gPsPd
-  return bwd + (2u << 20);
+  const size_t node_bufs = f(Rn * 256) + 5 * f(Rn * D);  // PsPd, aggr, N1..N3, Yn
+  const size_t scratch = 2u << 20;                        // packed weight / bias blocks
+  if (mode == BSMS_MODE_BF16 || (mode == BSMS_MODE_FP16X3 && !backward)) {
+    // fused tensor-core path: no per-edge buffer at all
+    if (!backward) return node_bufs + scratch;
+    return node_bufs + 2 * f(Rn * D) + 2 * f(Rn * 256) + scratch;
+  }
+  // fp32 path (and the fp32 backward the fp16x3 mode uses): per-edge activations are materialised
+  size_t fwd = node_bufs + f(Re * D) + scratch;
+  if (!backward) return fwd;
+  return node_bufs + 4 * f(Re * D) + 2 * f(Re * D) + 2 * f(Rn * D) + 2 * f(Rn * 256) + scratch;
 }
 
 static int check_common(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos,
