@@ -253,6 +253,62 @@ def run_mesh(args):
         dist.destroy_process_group()
 
 
+def run_rollout(args):
+    """BASELINE.json config 2 (CylinderFlow-like 44x44, unet_depth 5, B=1): T sequential processor
+    forwards with feedback, the reference's rollout pattern (src/utils/rollout_utils.py:48-62).
+    Reports ms per forward eagerly and replayed from a CUDA graph."""
+    from bsms_gnn_b200 import _lib
+    from bsms_gnn_b200.graphed import GraphedBSGMP
+    from bsms_gnn_b200.ops import BSGMP
+    from oracle import bsms_oracle as O
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    nx = args.nx if args.nx != 72 else 44
+    depth = args.depth if args.nx != 72 else 5
+    pos, m_gs, m_ids = build_workload(nx, depth)
+    E0 = int(m_gs[0].shape[1])
+    edge_rows = 2 * sum(int(g.shape[1]) for g in m_gs[:depth]) + int(m_gs[depth].shape[1])
+    mode = args.mode
+    model = BSGMP(depth, D, 3, 2, mode=mode).to(dev)
+    model.load_state_dict(O.init_params(depth, pos_dim=2, seed=0))
+    gs = [torch.from_numpy(g).to(dev) for g in m_gs]
+    ids = [torch.from_numpy(i).to(dev) for i in m_ids]
+    p = torch.from_numpy(pos).to(dev)
+    h0 = torch.randn(pos.shape[0], D, generator=torch.Generator().manual_seed(3)).to(dev)
+    T = max(args.steps, 10) if args.steps != 10 else 599
+    graphed = GraphedBSGMP(model, ids, gs, h0, p)
+
+    def timed(fn):
+        x = h0
+        for _ in range(args.warmup):
+            x = fn(x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _lib.launch_count()
+        e0.record()
+        x = h0
+        for _ in range(T):
+            x = fn(x)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / T, _lib.launch_count() - n0
+
+    with torch.no_grad():
+        ms_eager, launches = timed(lambda x: model(x, ids, gs, p))
+        ms_graph, _ = timed(lambda x: graphed(x))
+    print(json.dumps({
+        "metric": "M-edges/s per BSMS forward (rollout)", "value": E0 / (ms_graph * 1e-3) / 1e6, "unit": "M-edges/s",
+        "n_gpus": 1, "steps": T, "warmup": args.warmup, "ms_per_step": ms_graph, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": mode, "data": "synthetic",
+        "config": {"workload": f"cylinder-like {nx}x{nx} tri-grid ({pos.shape[0]} nodes / {E0} directed edges), "
+                               f"unet_depth {depth}, B=1, forward rollout of {T} sequential steps with feedback",
+                   "mode": mode, "execution": "CUDA graph replay"},
+        "ms_per_forward_eager": ms_eager, "ms_per_forward_graph": ms_graph,
+        "edge_evals_per_s": edge_rows / (ms_graph * 1e-3), "gpu_launches": int(launches),
+        "kernels_per_forward": launches / T}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -266,12 +322,14 @@ def main():
     ap.add_argument("--nx", type=int, default=72)
     ap.add_argument("--depth", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="airfoil", choices=["airfoil", "mesh"],
+    ap.add_argument("--workload", default="airfoil", choices=["airfoil", "mesh", "rollout"],
                     help="airfoil: BASELINE.json's metric config (batch-parallel over GPUs); mesh: one large "
                          "node-partitioned mesh, B=1 (config 5: --nx 1414 = 2.0 M nodes / 12.0 M edges)")
     args = ap.parse_args()
     if args.workload == "mesh":
         return run_mesh(args)
+    if args.workload == "rollout":
+        return run_rollout(args)
     assert args.warmup >= 3 or args.impl == "reference", "timing rules: at least 3 warm-up steps"
 
     rank = int(os.environ.get("RANK", "0"))
