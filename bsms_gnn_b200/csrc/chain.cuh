@@ -46,4 +46,17 @@ __global__ void k_pack_weights(PackList pl, uint8_t* __restrict__ out) {
 }
 
 
+// one weight-gradient problem dW[128, ldo] += G^T X over `rows` rows (node_gemm.cu)
+struct WgradParams {
+  const float* G;
+  int ldg;
+  const float* X;
+  int ldx;
+  float* dW;  // [128, ldo] accumulated
+  int ldo;
+  float* db;  // [128] accumulated, may be null
+  long long rows;
+  int ntiles;
+};
+
 }  // namespace bsms

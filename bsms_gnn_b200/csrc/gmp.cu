@@ -360,7 +360,7 @@ extern "C" size_t bsms_gmp_workspace_bytes(int32_t B, int32_t N, int32_t E, int3
   if (mode == BSMS_MODE_BF16 || (mode == BSMS_MODE_FP16X3 && !backward)) {
     // fused tensor-core path: no per-edge buffer at all
     if (!backward) return node_bufs + scratch;
-    return node_bufs + 2 * f(Rn * D) + 2 * f(Rn * 256) + scratch;
+    return node_bufs + 4 * f(Rn * D) + 2 * f(Rn * 256) + scratch;
   }
   // fp32 path (and the fp32 backward the fp16x3 mode uses): per-edge activations are materialised
   size_t fwd = node_bufs + f(Re * D) + scratch;

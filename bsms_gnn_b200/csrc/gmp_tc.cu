@@ -17,8 +17,8 @@ int gmp_pack_blocks(const PackList& pl, int mode, uint8_t* out, cudaStream_t st)
 int lin_tc(int mode, const float* X0, int ldx0, const float* X1, int ldx1, int KB, int NB, const uint8_t* const* blocks,
            int b_mn, const float* bias, int relu, const float* mask, int ldmask, int accum, float* Y, int ldy,
            long long rows, int kind, cudaStream_t st);
-int wgrad_tc(const float* G, int ldg, const float* X, int ldx, float* dW, int ldo, float* db, long long rows,
-             cudaStream_t st);
+int wgrad_tc_batch(const WgradParams* probs, int nprob, cudaStream_t st);
+WgradParams wgrad_problem(const float* G, int ldg, const float* X, int ldx, float* dW, int ldo, float* db, long long rows);
 int launch_ln_residual(const float* Yn, const float* x, const float* skip, float* out, long long rows, cudaStream_t st);
 int launch_ln_bwd_rows(const float* Y, const float* g, int ldg, float* gY, long long rows, cudaStream_t st);
 int launch_add_rows(const float* a, const float* b, int ldb, float* out, long long rows, cudaStream_t st);
@@ -142,6 +142,8 @@ int gmp_backward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const 
   NodeBufs n = carve_nodes(saved ? sv : ar, Rn);
   float* G1 = ar.take<float>(Rn * kD);
   float* G2 = ar.take<float>(Rn * kD);
+  float* G3 = ar.take<float>(Rn * kD);
+  float* G4 = ar.take<float>(Rn * kD);
   float* gcat = ar.take<float>(Rn * 256);
   float* gPsPd = ar.take<float>(Rn * 256);
   uint8_t* wpack = ar.take<uint8_t>(kScratchBytes);
@@ -153,37 +155,41 @@ int gmp_backward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const 
   auto blk = [&](int i) { return (const uint8_t*)(wpack + (size_t)i * bs); };
   TC_TRY(pack_all(w, P, mode, wpack, st));
   if (!saved) TC_TRY(forward_nodes(pl, w, x, pos, pos_batched, B, P, mode, n, wpack, st));
-  // ---- node MLP backward
-  TC_TRY(launch_ln_bwd_rows(n.Yn, g_out, kD, G1, Rn, st));  // gYn
-  TC_TRY(wgrad_tc(G1, kD, n.N3, kD, gr->w_node[3], kD, gr->b_node[3], Rn, st));
+  // ---- node MLP backward: the data-gradient chain first, then ALL weight gradients in one launch
+  TC_TRY(launch_ln_bwd_rows(n.Yn, g_out, kD, G1, Rn, st));  // G1 = gYn
   {
     const uint8_t* b[1] = {blk(BV4)};
     TC_TRY(lin_tc(mode, G1, kD, nullptr, 0, 1, 1, b, 1, nullptr, 0, n.N3, kD, 0, G2, kD, Rn, PK_DGRAD, st));
   }
-  TC_TRY(wgrad_tc(G2, kD, n.N2, kD, gr->w_node[2], kD, gr->b_node[2], Rn, st));
   {
     const uint8_t* b[1] = {blk(BV3)};
-    TC_TRY(lin_tc(mode, G2, kD, nullptr, 0, 1, 1, b, 1, nullptr, 0, n.N2, kD, 0, G1, kD, Rn, PK_DGRAD, st));
+    TC_TRY(lin_tc(mode, G2, kD, nullptr, 0, 1, 1, b, 1, nullptr, 0, n.N2, kD, 0, G3, kD, Rn, PK_DGRAD, st));
   }
-  TC_TRY(wgrad_tc(G1, kD, n.N1, kD, gr->w_node[1], kD, gr->b_node[1], Rn, st));
   {
     const uint8_t* b[1] = {blk(BV2)};
-    TC_TRY(lin_tc(mode, G1, kD, nullptr, 0, 1, 1, b, 1, nullptr, 0, n.N1, kD, 0, G2, kD, Rn, PK_DGRAD, st));
+    TC_TRY(lin_tc(mode, G3, kD, nullptr, 0, 1, 1, b, 1, nullptr, 0, n.N1, kD, 0, G4, kD, Rn, PK_DGRAD, st));
   }
-  // layer 0 of the node MLP: input [x | aggr]
-  TC_TRY(wgrad_tc(G2, kD, x, kD, gr->w_node[0], 2 * kD, gr->b_node[0], Rn, st));
-  TC_TRY(wgrad_tc(G2, kD, n.aggr, kD, gr->w_node[0] + kD, 2 * kD, nullptr, Rn, st));
   {
-    const uint8_t* b[2] = {blk(BV1A), blk(BV1B)};  // gcat = G2 V1 : [g_x part | g_aggr]
-    TC_TRY(lin_tc(mode, G2, kD, nullptr, 0, 1, 2, b, 1, nullptr, 0, nullptr, 0, 0, gcat, 256, Rn, PK_DGRAD, st));
+    WgradParams pr[5] = {
+        wgrad_problem(G1, kD, n.N3, kD, gr->w_node[3], kD, gr->b_node[3], Rn),
+        wgrad_problem(G2, kD, n.N2, kD, gr->w_node[2], kD, gr->b_node[2], Rn),
+        wgrad_problem(G3, kD, n.N1, kD, gr->w_node[1], kD, gr->b_node[1], Rn),
+        wgrad_problem(G4, kD, x, kD, gr->w_node[0], 2 * kD, gr->b_node[0], Rn),         // layer 0: input [x | aggr]
+        wgrad_problem(G4, kD, n.aggr, kD, gr->w_node[0] + kD, 2 * kD, nullptr, Rn)};
+    TC_TRY(wgrad_tc_batch(pr, 5, st));
+  }
+  {
+    const uint8_t* b[2] = {blk(BV1A), blk(BV1B)};  // gcat = G4 V1 : [g_x part | g_aggr]
+    TC_TRY(lin_tc(mode, G4, kD, nullptr, 0, 1, 2, b, 1, nullptr, 0, nullptr, 0, 0, gcat, 256, Rn, PK_DGRAD, st));
   }
   TC_TRY(launch_add_rows(g_out, gcat, 256, g_x, Rn, st));
   // ---- edge stage backward (fused) and the node-level gradients of the first edge layer
   if (Re > 0) {
     BSMS_CUDA(cudaMemsetAsync(gPsPd, 0, (size_t)Rn * 256 * sizeof(float), st));
     TC_TRY(edge_chain_backward(pl, w, gr, n.PsPd, pos, pos_batched, B, P, wpack, gcat + 128, 256, gPsPd, st, true));
-    TC_TRY(wgrad_tc(gPsPd, 256, x, kD, gr->w_edge[0] + (P + 1), ldw1, nullptr, Rn, st));
-    TC_TRY(wgrad_tc(gPsPd + 128, 256, x, kD, gr->w_edge[0] + (P + 1 + kD), ldw1, nullptr, Rn, st));
+    WgradParams pr[2] = {wgrad_problem(gPsPd, 256, x, kD, gr->w_edge[0] + (P + 1), ldw1, nullptr, Rn),
+                         wgrad_problem(gPsPd + 128, 256, x, kD, gr->w_edge[0] + (P + 1 + kD), ldw1, nullptr, Rn)};
+    TC_TRY(wgrad_tc_batch(pr, 2, st));
     const uint8_t* b[2] = {blk(BW1S), blk(BW1D)};  // g_x += gPs W1s + gPd W1d
     TC_TRY(lin_tc(mode, gPsPd, 256, gPsPd + 128, 256, 2, 1, b, 1, nullptr, 0, nullptr, 0, 1, g_x, kD, Rn, PK_DGRAD, st));
   }

@@ -165,24 +165,22 @@ __global__ void __launch_bounds__(128, 2) k_lin(const LinParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
-struct WgradParams {
-  const float* G;
-  int ldg;
-  const float* X;
-  int ldx;
-  float* dW;  // [128, ldo] accumulated
-  int ldo;
-  float* db;  // [128] accumulated, may be null
-  long long rows;
-  int ntiles;
+// several independent weight-gradient problems in one launch (CTA c works on problem c / ctas_per_prob)
+struct WgradBatch {
+  WgradParams prob[6];
+  int nprob;
+  int ctas_per_prob;
 };
 
 __device__ __forceinline__ uint32_t t_off(int r, int chunk) {
   return (uint32_t)((chunk >> 3) * 16384 + r * 128 + (((chunk & 7) ^ (r & 7)) << 4));
 }
 
-__global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradParams p) {
+__global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradBatch batch) {
   extern __shared__ uint8_t smem_raw[];
+  const int cpp = batch.ctas_per_prob;
+  const WgradParams p = batch.prob[blockIdx.x / cpp];
+  const int cta_in_prob = blockIdx.x % cpp;
   constexpr uint32_t IDESC_MM = make_idesc(1, 128, 128, 1, 1);
   const uint32_t s0 = smem_u32(smem_raw);
   const uint32_t sbase = (s0 + 1023u) & ~1023u;
@@ -207,7 +205,7 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradParams p) {
   float acc_b = 0.f;
   uint32_t ph[2] = {0u, 0u};
   int it = 0;
-  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+  for (int tile = cta_in_prob; tile < p.ntiles; tile += cpp, ++it) {
     const int s = it & 1;
     // the MMAs that read stage s two iterations ago must be done before it is overwritten
     if (it >= 2) {
@@ -348,9 +346,26 @@ int lin_tc(int mode, const float* X0, int ldx0, const float* X1, int ldx1, int K
   return BSMS_OK;
 }
 
-int wgrad_tc(const float* G, int ldg, const float* X, int ldx, float* dW, int ldo, float* db, long long rows,
-             cudaStream_t st) {
-  if (rows == 0) return BSMS_OK;
+// One launch for up to 6 weight-gradient problems over the same number of rows.
+int wgrad_tc_batch(const WgradParams* probs, int nprob, cudaStream_t st) {
+  if (nprob == 0 || probs[0].rows == 0) return BSMS_OK;
+  WgradBatch b;
+  b.nprob = nprob;
+  const int ntiles = ceil_div(probs[0].rows, 128);
+  for (int i = 0; i < nprob; ++i) {
+    b.prob[i] = probs[i];
+    b.prob[i].ntiles = ntiles;
+  }
+  b.ctas_per_prob = std::max(1, std::min(ntiles, sm_count() / nprob));
+  const size_t smem = 1024 + 4 * kWBlk + 64;
+  BSMS_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope ps_(PK_WGRAD, st);
+  k_wgrad_tc<<<b.ctas_per_prob * nprob, 256, smem, st>>>(b);
+  BSMS_LAUNCHED();
+  return BSMS_OK;
+}
+
+WgradParams wgrad_problem(const float* G, int ldg, const float* X, int ldx, float* dW, int ldo, float* db, long long rows) {
   WgradParams p;
   p.G = G;
   p.ldg = ldg;
@@ -360,13 +375,14 @@ int wgrad_tc(const float* G, int ldg, const float* X, int ldx, float* dW, int ld
   p.ldo = ldo;
   p.db = db;
   p.rows = rows;
-  p.ntiles = ceil_div(rows, 128);
-  const size_t smem = 1024 + 4 * kWBlk + 64;
-  BSMS_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ProfScope ps_(PK_WGRAD, st);
-  k_wgrad_tc<<<std::min(sm_count(), p.ntiles), 256, smem, st>>>(p);
-  BSMS_LAUNCHED();
-  return BSMS_OK;
+  p.ntiles = 0;
+  return p;
+}
+
+int wgrad_tc(const float* G, int ldg, const float* X, int ldx, float* dW, int ldo, float* db, long long rows,
+             cudaStream_t st) {
+  WgradParams p = wgrad_problem(G, ldg, X, ldx, dW, ldo, db, rows);
+  return wgrad_tc_batch(&p, 1, st);
 }
 
 }  // namespace bsms
