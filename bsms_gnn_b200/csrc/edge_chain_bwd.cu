@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
   float4* s_F = reinterpret_cast<float4*>(s_bias + 512);     // [128]
   float4* s_fib = s_F + 128;                                 // [128] fiber of each tile row
   float4* s_x = s_fib + 128;                                 // [2][128] LayerNorm partial sums
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_x + 256);
+  int* s_tgt = reinterpret_cast<int*>(s_x + 256);            // [128] destination row (b*N + dst) of each tile row
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tgt + 128);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
   const uint32_t aW[3] = {sbase, sbase + kWBlk, sbase + 2 * kWBlk};
   const uint32_t aT[3] = {sbase + 3 * kWBlk, sbase + 4 * kWBlk, sbase + 5 * kWBlk};
@@ -196,7 +197,10 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       }
       fib[p.P] = sqrtf(nrm);
     }
-    if (h == 0) s_fib[r] = make_float4(fib[0], fib[1], fib[2], fib[3]);
+    if (h == 0) {
+      s_fib[r] = make_float4(fib[0], fib[1], fib[2], fib[3]);
+      s_tgt[r] = valid ? b * p.N + j : -1;
+    }
     const float* ps_row = p.PsPd + ((size_t)b * p.N + i) * 256 + 64 * h;
     const float* pd_row = p.PsPd + ((size_t)b * p.N + j) * 256 + 128 + 64 * h;
     uint32_t m0[2] = {0u, 0u}, m1[2] = {0u, 0u}, m2[2] = {0u, 0u};
@@ -384,7 +388,6 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     // ---- g0 = D . m0 : scatter to the projected-row gradients, stage in T2 for gb1 / gF
     {
       float* gs = p.gPsPd + ((size_t)b * p.N + i) * 256 + 64 * h;
-      float* gd = p.gPsPd + ((size_t)b * p.N + j) * 256 + 128 + 64 * h;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t rr_[32];
@@ -397,7 +400,6 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
 #pragma unroll
           for (int q4 = 0; q4 < 8; ++q4) {
             red_add_v4(gs + 32 * hh + q4 * 4, v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
-            red_add_v4(gd + 32 * hh + q4 * 4, v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
           }
         }
         store32(s_T[2], 8 * h + 4 * hh, v);
@@ -405,14 +407,28 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     }
     __syncthreads();
     {
+      // channel-owner pass over the staged g0 tile: bias / fiber-weight column sums AND the gradient
+      // of the receiver projection, gPd[dst] += g0, reduced over runs of equal dst (the rows are
+      // dst-sorted) so that one red.add per (run, channel) reaches L2 instead of one per edge
       float sb = 0.f, sf0 = 0.f, sf1 = 0.f, sf2 = 0.f, sf3 = 0.f;
+      float run = 0.f;
+      int cur = s_tgt[rh * 64];
+      float* gdc = p.gPsPd + 128 + cc;
 #pragma unroll 8
       for (int rr = rh * 64; rr < rh * 64 + 64; ++rr) {
         const float gv = tile_elem(s_T[2], rr, cc);
         const float4 f = s_fib[rr];
+        const int t_ = s_tgt[rr];
+        if (t_ != cur) {
+          if (cur >= 0) atomicAdd(gdc + (size_t)cur * 256, run);
+          cur = t_;
+          run = 0.f;
+        }
+        run += gv;
         sb += gv;
         sf0 += gv * f.x; sf1 += gv * f.y; sf2 += gv * f.z; sf3 += gv * f.w;
       }
+      if (cur >= 0) atomicAdd(gdc + (size_t)cur * 256, run);
       acc_b[0] += sb;
       acc_f[0] += sf0; acc_f[1] += sf1; acc_f[2] += sf2; acc_f[3] += sf3;
     }
@@ -446,7 +462,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-size_t edge_chain_bwd_smem() { return 1024 + 6 * kWBlk + 512 * 4 + 128 * 16 * 2 + 256 * 16 + 2 * 8 + 16; }
+size_t edge_chain_bwd_smem() { return 1024 + 6 * kWBlk + 512 * 4 + 128 * 16 * 2 + 256 * 16 + 128 * 4 + 2 * 8 + 16; }
 
 // Fused bf16 backward of the edge stage.  gPsPd must be zero-filled; gW/gb/gW1 are accumulated into.
 int edge_chain_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const bsms_gmp_grads* gr, const float* PsPd,
