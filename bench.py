@@ -457,10 +457,15 @@ def main():
         #   FLOPs for the dense kernels, gather-counted bytes for the bandwidth kernels
         flops = {"edge_fwd_gemm": fwd_passes * Re * 3 * 2 * D * D, "dgrad": (Re * 3 + Rn * 7) * 2 * D * D,
                  "wgrad": (Re * 3 + Rn * 8) * 2 * D * D, "node_fwd_gemm": 2 * Rn * 7 * 2 * D * D,
-                 "edge_chain": Re * 3 * 2 * D * D}
+                 "edge_chain": Re * 3 * 2 * D * D,
+                 "edge_chain_bwd": Re * 9 * 2 * D * D}  # 3 recompute + 3 data-gradient + 3 weight-gradient GEMMs
         byts = {"edge_combine": 2 * (Re * (2 * D * 4 + 16 + 8 + D * 4)), "ln_segsum": 2 * (Re * D * 4 + Rn * D * 4),
                 "ln_bwd": Re * 3 * D * 4 + Rn * 3 * D * 4, "edge_grad_segsum": 2 * Re * D * 4 + Rn * 2 * D * 4,
-                "edge_chain": Re * (2 * D * 4 + 2 * 2 * 4 + 2 * 4) + Rn * D * 4}
+                "edge_chain": Re * (2 * D * 4 + 2 * 2 * 4 + 2 * 4) + Rn * D * 4,
+                # backward: the two projected rows are gathered twice (a0 is re-formed for its weight gradient),
+                # one upstream-gradient row is gathered, one gradient row is scattered per edge (sender side),
+                # the receiver side is reduced per destination run first
+                "edge_chain_bwd": Re * (4 * D * 4 + D * 4 + 2 * 2 * 4 + 2 * 4 + D * 4) + Rn * D * 4}
         breakdown = {k: {"ms_per_step": v[0] / prof_steps, "launches_per_step": v[1] / prof_steps}
                      for k, v in prof.items() if v[1]}
         total_ms = sum(v["ms_per_step"] for v in breakdown.values())
@@ -469,7 +474,7 @@ def main():
             tms = breakdown[kind]["ms_per_step"]
             r = {"kernel": kind, "share_of_step": tms / total_ms, "traffic": None,
                  "avg_launch_us": 1e3 * tms / breakdown[kind]["launches_per_step"]}
-            if kind == "edge_chain" and args.mode == "bf16":
+            if kind in ("edge_chain", "edge_chain_bwd") and args.mode == "bf16":
                 # 1x bf16 MMA: HBM (gather-counted) is the governing bound, SURVEY.md §8d
                 ach = byts[kind] / (tms * 1e-3) / 1e9
                 r.update(bound="hbm", achieved=ach, peak=pk["hbm_gbs"], unit="GB/s", frac=ach / pk["hbm_gbs"],
@@ -496,8 +501,20 @@ def main():
 
         top = max(breakdown, key=lambda k: breakdown[k]["ms_per_step"])
         roofline = roof(top)
+        # DRAM traffic of the same kernel from the committed ncu --set full capture (per launch, level 0)
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        traffic_db = json.load(open(tpath)) if os.path.exists(tpath) else {}
+
+        def add_traffic(r):
+            tj = traffic_db.get(r["kernel"]) if r else None
+            if tj:
+                r["traffic"] = tj["dram_bytes_per_launch"]
+                r["traffic_note"] = tj["note"]
+
+        add_traffic(roofline)
         if "edge_chain" in breakdown and top != "edge_chain":
             roofline_edge = roof("edge_chain")
+            add_traffic(roofline_edge)
         else:
             roofline_edge = None
 

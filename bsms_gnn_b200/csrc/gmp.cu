@@ -424,7 +424,7 @@ extern "C" int bsms_gmp_backward(const bsms_level_plan* pl, const bsms_gmp_weigh
   const long long Rn = (long long)B * N, Re = (long long)B * E;
   const int ldw1 = 2 * D + P + 1;
   Arena ar(ws, ws_bytes);
-  const bool fused = (mode == BSMS_MODE_BF16);  // fused tcgen05 edge backward; the split modes use the fp32 path
+  const bool fused = false;  // BSMS_MODE_BF16 was dispatched to gmp_backward_tc above; fp32 / fp16x3 backward run here
   // with `saved` from forward the fused path recomputes nothing at node level
   const bool have_saved = fused && saved != nullptr;
   Fp32Acts a = carve(ar, Rn, Re, true, !fused, have_saved ? const_cast<float*>(saved) : nullptr);
