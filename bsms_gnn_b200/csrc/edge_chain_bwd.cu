@@ -274,6 +274,24 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       }
     };
 
+    // ---- pull the next tile's gather rows (projected rows, upstream gradient row) into L2 early
+    {
+      const long long nrow = row + (long long)gridDim.x * 128;
+      if (nrow < p.rows && h == 0) {
+        const int nb = (int)(nrow / p.E);
+        const int ne = (int)(nrow - (long long)nb * p.E);
+        const int ni = p.src_d[ne], nj = p.dst_d[ne];
+        const float* nps = p.PsPd + ((size_t)nb * p.N + ni) * 256;
+        const float* npd = p.PsPd + ((size_t)nb * p.N + nj) * 256 + 128;
+        const float* ng = p.g_aggr + ((size_t)nb * p.N + nj) * p.ld_g;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nps + k * 32));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(npd + k * 32));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ng + k * 32));
+        }
+      }
+    }
     // ---- recompute the forward chain
     gather_a0(s_T[0], m0);
     sync_all();

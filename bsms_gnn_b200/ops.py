@@ -108,7 +108,9 @@ class _GMPFunction(torch.autograd.Function):
         B, N, _ = x3.shape
         g_out = g_out.contiguous()
         g_x = torch.empty_like(x3)
-        grads = [torch.zeros_like(p) for p in params]
+        # one zero-filled flat buffer for the 16 parameter gradients (the kernels accumulate into them)
+        flat = torch.zeros(sum(p.numel() for p in params), dtype=params[0].dtype, device=x3.device)
+        grads = [v.view_as(p) for v, p in zip(flat.split([p.numel() for p in params]), params)]
         nbytes = int(lib.bsms_gmp_workspace_bytes(B, N, level.n_edges, mode, 1))
         ws = _lib.workspace(nbytes, x3.device)
         w, gw = _weights_struct(params), _weights_struct(grads)
