@@ -16,6 +16,48 @@ __host__ __device__ inline uint32_t wblk_offset(int n, int k) {
   return (uint32_t)((k >> 6) * 16384 + n * 128 + ((((k & 63) >> 3) ^ (n & 7)) << 4) + (k & 7) * 2);
 }
 
+// Row-cooperative gather of the first edge activation a0 = relu(Ps[src] + Pd[dst] + F fiber) into a
+// K-major SWIZZLE_128B bf16 operand tile ([row][channel], the layout of wblk_offset): ONE WARP PER
+// ROW, lane l owns channels 4l..4l+3, so every global load is a coalesced 512 B row (4 L1 wavefronts
+// instead of the 32 a lane-per-row gather costs) and U rows (2U loads) are in flight per warp.
+// s_ij[r] = (b*N+src, b*N+dst) of tile row r, (-1, -1) for rows past the end (their fiber is 0 and
+// the tile row is zero-filled); Fl[c] = fiber coefficients of channel 4l+c.
+template <int U>
+__device__ __forceinline__ void coop_gather_a0(const float* __restrict__ PsPd, const int2* s_ij, const float4* s_fib,
+                                               const float4 (&Fl)[4], uint8_t* tile, int r_begin, int r_end, int lane,
+                                               float* dbg, long long dbg_row0) {
+  const uint32_t col_off = (uint32_t)((lane >> 4) * 16384 + (lane & 1) * 8);
+  const int chunk7 = (lane >> 1) & 7;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int r = r_begin; r < r_end; r += U) {
+    float4 a[U], d[U];
+    int ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int2 ij = s_ij[r + u];
+      ok[u] = ij.x >= 0;
+      a[u] = ok[u] ? ld4(PsPd + (size_t)ij.x * 256 + 4 * lane) : z4;
+      d[u] = ok[u] ? ld4(PsPd + (size_t)ij.y * 256 + 128 + 4 * lane) : z4;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float4 f = s_fib[r + u];
+      float x0 = a[u].x + d[u].x, x1 = a[u].y + d[u].y, x2 = a[u].z + d[u].z, x3 = a[u].w + d[u].w;
+      x0 = x0 + Fl[0].x * f.x + Fl[0].y * f.y + Fl[0].z * f.z + Fl[0].w * f.w;
+      x1 = x1 + Fl[1].x * f.x + Fl[1].y * f.y + Fl[1].z * f.z + Fl[1].w * f.w;
+      x2 = x2 + Fl[2].x * f.x + Fl[2].y * f.y + Fl[2].z * f.z + Fl[2].w * f.w;
+      x3 = x3 + Fl[3].x * f.x + Fl[3].y * f.y + Fl[3].z * f.z + Fl[3].w * f.w;
+      x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+      if (dbg && ok[u]) st4(dbg + (dbg_row0 + r + u) * 128 + 4 * lane, make_float4(x0, x1, x2, x3));
+      uint2 pk;
+      pk.x = pack_bf16(x0, x1);
+      pk.y = pack_bf16(x2, x3);
+      *reinterpret_cast<uint2*>(tile + col_off + (r + u) * 128 + ((chunk7 ^ ((r + u) & 7)) << 4)) = pk;
+    }
+  }
+}
+
 struct PackList {
   const float* w[12];
   int ld[12];

@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
   extern __shared__ uint8_t smem_raw[];
   constexpr int NW = 3 * NSPLIT;
   constexpr bool BIAS_MMA = (NSPLIT == 1);
+  constexpr bool COOP = (NSPLIT == 1);  // row-cooperative (coalesced) gather into a shared-memory a0 tile
   constexpr uint32_t FMT = (NSPLIT == 1) ? 1u : 0u;  // bf16 : f16
   constexpr uint32_t IDESC = make_idesc(FMT, 128, 128);
   constexpr float OUT_SCALE = (NSPLIT == 1) ? 1.f : 1.f / (kActScale * kWScale);
@@ -92,11 +93,17 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
   const uint32_t sbase = (s0 + 1023u) & ~1023u;
   uint8_t* sp = smem_raw + (sbase - s0);
   const uint32_t bias_blk = sbase + NW * kWBlk;                       // 3 x 16 KB (bf16 mode only)
-  uint8_t* sp2 = sp + NW * kWBlk + (BIAS_MMA ? 3 * kBiasBlk : 0);
+  // bf16 mode: one 32 KB a0 operand tile per warpgroup (row-cooperative gather, SS-form first MMA); the
+  // segmented-reduce staging of the same warpgroup aliases it (a0 is dead once the first MMA completes)
+  const uint32_t a0_blk = bias_blk + 3 * kBiasBlk;
+  uint8_t* s_a0 = sp + NW * kWBlk + 3 * kBiasBlk;
+  uint8_t* sp2 = sp + NW * kWBlk + (BIAS_MMA ? 3 * kBiasBlk : 0) + (COOP ? 2 * kWBlk : 0);
   float* s_bias = reinterpret_cast<float*>(sp2);         // [3][128]: b2, b3, b4 (fp16x3 mode)
   float4* s_F = reinterpret_cast<float4*>(s_bias + 384);  // [128]
-  float* s_stage = reinterpret_cast<float*>(s_F + 128);   // [8][32][CH+1]
-  int* s_tgt = reinterpret_cast<int*>(s_stage + 8 * 32 * (CH + 1));
+  float4* s_fib = s_F + 128;                              // [256] fiber of each tile row (bf16 mode)
+  int2* s_ij = reinterpret_cast<int2*>(s_fib + 256);      // [256] (b*N+src, b*N+dst) of each tile row
+  float* s_stage = reinterpret_cast<float*>(s_ij + 256);  // [8][32][CH+1] (fp16x3 mode)
+  int* s_tgt = reinterpret_cast<int*>(s_stage + (COOP ? 0 : 8 * 32 * (CH + 1)));
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tgt + 256);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 3);
 
@@ -144,8 +151,11 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
   }
   uint32_t phase = 0;
   bool weights_ready = false;
-  float* stage = s_stage + warp * 32 * (CH + 1);
+  float* stage = COOP ? reinterpret_cast<float*>(s_a0 + wg * kWBlk) + q * 32 * (CH + 1) : s_stage + warp * 32 * (CH + 1);
   int* tgt = s_tgt + warp * 32;
+  float4 Fl[4];  // fiber coefficients of this lane's 4 channels (row-cooperative gather)
+#pragma unroll
+  for (int c = 0; c < 4; ++c) Fl[c] = s_F[4 * lane + c];
 
   for (int tile = blockIdx.x * 2 + wg; tile < p.ntiles; tile += gridDim.x * 2) {
     const long long row = (long long)tile * 128 + tw;
@@ -176,41 +186,52 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
       }
       fib[p.P] = sqrtf(nrm);
     }
-    const float* ps_row = p.PsPd + ((size_t)b * p.N + i) * 256;
-    const float* pd_row = p.PsPd + ((size_t)b * p.N + j) * 256 + 128;
-    float4 ga[8], gd[8];
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int q4 = 0; q4 < 8; ++q4) {
-      ga[q4] = valid ? ld4(ps_row + q4 * 4) : z4;
-      gd[q4] = valid ? ld4(pd_row + q4 * 4) : z4;
-    }
-#pragma unroll
-    for (int c0 = 0; c0 < 128; c0 += 32) {
-      float v[32];
-#pragma unroll
+    if constexpr (COOP) {
+      // the staging region of the previous tile's segmented reduce aliases the a0 tile
+      bar_sync(1 + wg, 128);
+      s_ij[wg * 128 + tw] = valid ? make_int2(b * p.N + i, b * p.N + j) : make_int2(-1, -1);
+      s_fib[wg * 128 + tw] = make_float4(fib[0], fib[1], fib[2], fib[3]);
+      __syncwarp();
+      coop_gather_a0<8>(p.PsPd, s_ij + wg * 128, s_fib + wg * 128, Fl, s_a0 + wg * kWBlk, q * 32, q * 32 + 32, lane,
+                        p.dbg_stage == 0 ? p.dbg : nullptr, (long long)tile * 128);
+      fence_proxy_async();
+    } else {
+      const float* ps_row = p.PsPd + ((size_t)b * p.N + i) * 256;
+      const float* pd_row = p.PsPd + ((size_t)b * p.N + j) * 256 + 128;
+      float4 ga[8], gd[8];
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  #pragma unroll
       for (int q4 = 0; q4 < 8; ++q4) {
-        v[q4 * 4 + 0] = ga[q4].x + gd[q4].x; v[q4 * 4 + 1] = ga[q4].y + gd[q4].y;
-        v[q4 * 4 + 2] = ga[q4].z + gd[q4].z; v[q4 * 4 + 3] = ga[q4].w + gd[q4].w;
+        ga[q4] = valid ? ld4(ps_row + q4 * 4) : z4;
+        gd[q4] = valid ? ld4(pd_row + q4 * 4) : z4;
       }
-      if (c0 + 32 < 128) {
-#pragma unroll
+  #pragma unroll
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        float v[32];
+  #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4) {
-          ga[q4] = valid ? ld4(ps_row + c0 + 32 + q4 * 4) : z4;
-          gd[q4] = valid ? ld4(pd_row + c0 + 32 + q4 * 4) : z4;
+          v[q4 * 4 + 0] = ga[q4].x + gd[q4].x; v[q4 * 4 + 1] = ga[q4].y + gd[q4].y;
+          v[q4 * 4 + 2] = ga[q4].z + gd[q4].z; v[q4 * 4 + 3] = ga[q4].w + gd[q4].w;
         }
+        if (c0 + 32 < 128) {
+  #pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            ga[q4] = valid ? ld4(ps_row + c0 + 32 + q4 * 4) : z4;
+            gd[q4] = valid ? ld4(pd_row + c0 + 32 + q4 * 4) : z4;
+          }
+        }
+  #pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          float4 f = s_F[c0 + t];
+          float x = v[t] + f.x * fib[0] + f.y * fib[1] + f.z * fib[2] + f.w * fib[3];
+          v[t] = fmaxf(x, 0.f);
+        }
+        if (p.dbg && p.dbg_stage == 0 && valid) {
+  #pragma unroll
+          for (int t = 0; t < 32; ++t) p.dbg[row * 128 + c0 + t] = v[t];
+        }
+        store_act32<NSPLIT>(a_tmem + lane_off, c0, v);
       }
-#pragma unroll
-      for (int t = 0; t < 32; ++t) {
-        float4 f = s_F[c0 + t];
-        float x = v[t] + f.x * fib[0] + f.y * fib[1] + f.z * fib[2] + f.w * fib[3];
-        v[t] = fmaxf(x, 0.f);
-      }
-      if (p.dbg && p.dbg_stage == 0 && valid) {
-#pragma unroll
-        for (int t = 0; t < 32; ++t) p.dbg[row * 128 + c0 + t] = v[t];
-      }
-      store_act32<NSPLIT>(a_tmem + lane_off, c0, v);
     }
     // ---- pull the NEXT tile's projected rows into L2 while this tile computes (half of the gathers
     //      miss L2 otherwise: lts hit rate 48 % under ncu), 16 x 128 B lines per thread
@@ -247,7 +268,10 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
         for (int ks = 0; ks < 8; ++ks) {
           const uint32_t koff = (ks >> 2) * 16384 + (ks & 3) * 32;
           const uint64_t bhi = smem_desc_sw128(wb + koff, 16, 1024);
-          mma_ts(d_tmem, a_tmem + ks * 8, bhi, IDESC, (BIAS_MMA || ks > 0) ? 1u : 0u);
+          if (COOP && layer == 0)
+            mma_ss(d_tmem, smem_desc_sw128(a0_blk + wg * kWBlk + koff, 16, 1024), bhi, IDESC, 1u);
+          else
+            mma_ts(d_tmem, a_tmem + ks * 8, bhi, IDESC, (BIAS_MMA || ks > 0) ? 1u : 0u);
           if (NSPLIT == 2) {
             const uint64_t blo = smem_desc_sw128(wb + kWBlk + koff, 16, 1024);
             mma_ts(d_tmem, a_tmem + 64 + ks * 8, bhi, IDESC, 1);
@@ -354,8 +378,8 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
 
 template <int NSPLIT, int CH>
 static size_t edge_chain_smem() {
-  return 1024 + 3 * NSPLIT * kWBlk + (NSPLIT == 1 ? 3 * kBiasBlk : 0) + 384 * 4 + 128 * 16 + 8 * 32 * (CH + 1) * 4 +
-         256 * 4 + 3 * 8 + 16;
+  return 1024 + 3 * NSPLIT * kWBlk + (NSPLIT == 1 ? 3 * kBiasBlk + 2 * kWBlk : 0) + 384 * 4 + 128 * 16 + 256 * 16 + 256 * 8 +
+         (NSPLIT == 1 ? 0 : 8 * 32 * (CH + 1) * 4) + 256 * 4 + 3 * 8 + 16;
 }
 
 size_t edge_chain_pack_bytes(int mode) { return (size_t)3 * (mode == BSMS_MODE_FP16X3 ? 2 : 1) * kWBlk + 3 * kBiasBlk; }

@@ -4,14 +4,14 @@
 //
 // Per 128-edge tile (one tile per CTA at a time, persistent grid, 256 threads = 2 threads per edge
 // row: thread (row r, half h) owns channels [64h, 64h+64) of TMEM lane r):
-//   a0 = relu(Ps[src]+Pd[dst]+b1+F fiber)            gather            -> T0 (bf16 smem tile), mask m0
+//   a0 = relu(Ps[src]+Pd[dst]+b1+F fiber)            row-cooperative gather (one warp per 512 B row) -> T0 (bf16 smem tile)
 //   a1 = relu(a0 W2^T + b2)                           UMMA  D=T0 x W2   -> T1, m1
 //   a2 = relu(a1 W3^T + b3)                           UMMA  D=T1 x W3   -> T2, m2
 //   y  = a2 W4^T + b4 ; gy = LN'(y) * g_aggr[dst]     UMMA  D=T2 x W4   -> T0 (a0 is re-gathered later)
 //   dW4 += gy^T a2 ; g2 = (gy W4) . m2                UMMA  wgrad(T0,T2), dgrad D=T0 x W4(MN)  -> T2
 //   dW3 += g2^T a1 ; g1 = (g2 W3) . m1                UMMA  wgrad(T2,T1), dgrad D=T2 x W3(MN)  -> T1 ; a0 -> T0
-//   dW2 += g1^T a0 ; g0 = (g1 W2) . m0                UMMA  wgrad(T1,T0), dgrad D=T1 x W2(MN)
-//   gPs[src] += g0 ; gPd[dst] += g0 (red.add.v4) ; gF += g0^T fiber ; gb* += column sums
+//   dW2 += g1^T a0 ; g0 = (g1 W2) . [a0>0]            UMMA  wgrad(T1,T0), dgrad D=T1 x W2(MN)  -> fp32 staging over T1|T2
+//   gPs[src] += g0 (one coalesced 512 B red.add.v4 per row) ; gPd[dst] += run sums of g0 ; gF += g0^T fiber ; gb* += column sums
 // The three weight-gradient accumulators (3 x 128 TMEM columns) stay resident in tensor memory for
 // the whole persistent loop and are reduced into global memory once per CTA; the activation /
 // gradient tiles are written once in the canonical 128B-swizzled layout and consumed BOTH as
@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
   float4* s_F = reinterpret_cast<float4*>(s_bias + 512);     // [128]
   float4* s_fib = s_F + 128;                                 // [128] fiber of each tile row
   float4* s_x = s_fib + 128;                                 // [2][128] LayerNorm partial sums
-  int* s_tgt = reinterpret_cast<int*>(s_x + 256);            // [128] destination row (b*N + dst) of each tile row
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tgt + 128);
+  int2* s_ij = reinterpret_cast<int2*>(s_x + 256);           // [128] (b*N+src, b*N+dst) of each tile row, -1 past the end
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_ij + 128);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
   const uint32_t aW[3] = {sbase, sbase + kWBlk, sbase + 2 * kWBlk};
   const uint32_t aT[3] = {sbase + 3 * kWBlk, sbase + 4 * kWBlk, sbase + 5 * kWBlk};
@@ -134,8 +134,13 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
   uint32_t wacc = 0;  // weight-gradient accumulators hold something
   // persistent per-thread partial sums for the bias / fiber-weight gradients (channel cc, row half rh)
   const int cc = tid & 127, rh = tid >> 7;
-  float acc_b[4] = {0.f, 0.f, 0.f, 0.f};
-  float acc_f[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc_b[4] = {0.f, 0.f, 0.f, 0.f};  // [0] unused: gb1 / gF are accumulated per lane below
+  // row-cooperative passes: lane l owns channels 4l..4l+3
+  float4 acc_b0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc_fl[4];  // [fiber component k] x 4 channels
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc_fl[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float* s_g0 = reinterpret_cast<float*>(s_T[1]);  // fp32 [128][128] staging of g0 over T1|T2 (64 KB)
 
   // one full-CTA phase boundary: make generic smem writes visible to the tensor core, order tcgen05 ops
   auto sync_all = [&]() {
@@ -176,36 +181,42 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     acc += s;
   };
 
+  auto gather_a0 = [&]() {
+    float4 Fl[4];  // fiber coefficients of this lane's 4 channels
+#pragma unroll
+    for (int c = 0; c < 4; ++c) Fl[c] = s_F[4 * lane + c];
+    coop_gather_a0<8>(p.PsPd, s_ij, s_fib, Fl, s_T[0], warp * 16, warp * 16 + 16, lane, nullptr, 0);
+  };
+
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    // ---- row metadata (first 128 threads: one tile row each), then everything reads it from smem
+    if (tid < 128) {
+      const long long row_ = (long long)tile * 128 + tid;
+      float fib_[4] = {0.f, 0.f, 0.f, 0.f};
+      int2 ij = make_int2(-1, -1);
+      if (row_ < p.rows) {
+        const int b_ = (int)(row_ / p.E);
+        const int e_ = (int)(row_ - (long long)b_ * p.E);
+        const int i_ = p.src_d[e_], j_ = p.dst_d[e_];
+        const float* pb = p.pos + (p.pos_batched ? (size_t)b_ * p.N * p.P : 0);
+        float nrm = 0.f;
+        for (int k = 0; k < p.P; ++k) {
+          float dlt = pb[(size_t)i_ * p.P + k] - pb[(size_t)j_ * p.P + k];
+          fib_[k] = dlt;
+          nrm += dlt * dlt;
+        }
+        fib_[p.P] = sqrtf(nrm);
+        ij = make_int2(b_ * p.N + i_, b_ * p.N + j_);
+      }
+      s_fib[tid] = make_float4(fib_[0], fib_[1], fib_[2], fib_[3]);
+      s_ij[tid] = ij;
+    }
+    __syncthreads();
     const long long row = (long long)tile * 128 + r;
     const bool valid = row < p.rows;
-    int b = 0, i = 0, j = 0;
-    if (valid) {
-      b = (int)(row / p.E);
-      int e = (int)(row - (long long)b * p.E);
-      i = p.src_d[e];
-      j = p.dst_d[e];
-    }
-    float fib[4] = {0.f, 0.f, 0.f, 0.f};
-    if (valid) {
-      const float* pb = p.pos + (p.pos_batched ? (size_t)b * p.N * p.P : 0);
-      float nrm = 0.f;
-      for (int k = 0; k < p.P; ++k) {
-        float dlt = pb[(size_t)i * p.P + k] - pb[(size_t)j * p.P + k];
-        fib[k] = dlt;
-        nrm += dlt * dlt;
-      }
-      fib[p.P] = sqrtf(nrm);
-    }
-    if (h == 0) {
-      s_fib[r] = make_float4(fib[0], fib[1], fib[2], fib[3]);
-      s_tgt[r] = valid ? b * p.N + j : -1;
-    }
-    const float* ps_row = p.PsPd + ((size_t)b * p.N + i) * 256 + 64 * h;
-    const float* pd_row = p.PsPd + ((size_t)b * p.N + j) * 256 + 128 + 64 * h;
-    uint32_t m0[2] = {0u, 0u}, m1[2] = {0u, 0u}, m2[2] = {0u, 0u};
+    const int rowj = s_ij[r].y;
+    uint32_t m1[2] = {0u, 0u}, m2[2] = {0u, 0u};
 
-    // a0 (gather) -> dst tile; returns the ReLU mask
     // 32 fp32 values -> bf16 -> chunks [chunk0, chunk0+4) of row r
     auto store32 = [&](uint8_t* tile, int chunk0, const float (&v)[32]) {
 #pragma unroll
@@ -217,29 +228,6 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       }
     };
     // every phase handles this thread's 64 channels as two halves of 32 (register budget)
-    auto gather_a0 = [&](uint8_t* dst_tile, uint32_t (&mask)[2]) {
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        float v[32];
-#pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4) {
-          float4 a = valid ? ld4(ps_row + 32 * hh + q4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          float4 d = valid ? ld4(pd_row + 32 * hh + q4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          v[q4 * 4 + 0] = a.x + d.x; v[q4 * 4 + 1] = a.y + d.y; v[q4 * 4 + 2] = a.z + d.z; v[q4 * 4 + 3] = a.w + d.w;
-        }
-        uint32_t mk = 0u;
-#pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          float4 f = s_F[64 * h + 32 * hh + t];
-          float x = v[t] + f.x * fib[0] + f.y * fib[1] + f.z * fib[2] + f.w * fib[3];
-          const bool on = valid && x > 0.f;
-          v[t] = on ? x : 0.f;
-          mk |= (on ? 1u : 0u) << t;
-        }
-        mask[hh] = mk;
-        store32(dst_tile, 8 * h + 4 * hh, v);
-      }
-    };
     // activation epilogue: D + bias -> ReLU -> tile, mask
     auto act_epilogue = [&](const float* bias, uint8_t* dst_tile, uint32_t (&mask)[2]) {
 #pragma unroll
@@ -293,7 +281,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       }
     }
     // ---- recompute the forward chain
-    gather_a0(s_T[0], m0);
+    gather_a0();
     sync_all();
     if (tid == 0) {
       issue_gemm(aT[0], aW[0], false);
@@ -316,7 +304,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     // upstream gradient row g_aggr[dst] (this thread's 64 channels): issued before the MMA wait
     float g[64];
     {
-      const float* grow = p.g_aggr + ((size_t)b * p.N + j) * p.ld_g + 64 * h;
+      const float* grow = p.g_aggr + (size_t)(valid ? rowj : 0) * p.ld_g + 64 * h;
 #pragma unroll
       for (int q4 = 0; q4 < 16; ++q4) {
         float4 gv = valid ? ld4(grow + q4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -388,10 +376,8 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       mma_commit(bar_m);
     }
     colsum(s_T[2], acc_b[2]);
-    {
-      uint32_t mtmp[2];
-      gather_a0(s_T[0], mtmp);  // a0 again (T0 was reused for gy)
-    }
+    // a0 again (T0 was reused for gy); the generic-proxy writes are fenced by the next sync_all
+    gather_a0();
     wait_mma();
     grad_epilogue(m1, s_T[1]);  // g1 -> T1
     sync_all();
@@ -403,54 +389,61 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     }
     colsum(s_T[1], acc_b[1]);
     wait_mma();
-    // ---- g0 = D . m0 : scatter to the projected-row gradients, stage in T2 for gb1 / gF
+    // ---- g0 = D . [a0 > 0] (mask re-derived from the a0 tile) -> fp32 staging over T1|T2, 16-byte
+    //      chunks XOR-swizzled by row so that both the row-thread writes and the row-cooperative reads
+    //      below are bank-conflict free
+    __syncthreads();  // every thread is done with the column sums over T1 (g1) before it is overwritten
     {
-      float* gs = p.gPsPd + ((size_t)b * p.N + i) * 256 + 64 * h;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t rr_[32];
         tmem_ld32(d_mine + 32 * hh, rr_);
         wait_ld();
-        float v[32];
 #pragma unroll
-        for (int t = 0; t < 32; ++t) v[t] = ((m0[hh] >> t) & 1u) ? __uint_as_float(rr_[t]) : 0.f;
-        if (valid) {
+        for (int jj = 0; jj < 4; ++jj) {
+          const uint4 a8 = *reinterpret_cast<const uint4*>(s_T[0] + tile_off(r, 8 * h + 4 * hh + jj));
+          const uint32_t aw[4] = {a8.x, a8.y, a8.z, a8.w};
+          float o8[8];
 #pragma unroll
-          for (int q4 = 0; q4 < 8; ++q4) {
-            red_add_v4(gs + 32 * hh + q4 * 4, v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
+          for (int e = 0; e < 8; ++e) {
+            const uint32_t hw = (aw[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
+            o8[e] = hw ? __uint_as_float(rr_[8 * jj + e]) : 0.f;
           }
+          const int c4 = 16 * h + 8 * hh + 2 * jj;  // logical 16-byte chunk of the fp32 row
+          *reinterpret_cast<float4*>(s_g0 + r * 128 + (((c4 + 0) ^ (r & 31)) << 2)) = make_float4(o8[0], o8[1], o8[2], o8[3]);
+          *reinterpret_cast<float4*>(s_g0 + r * 128 + (((c4 + 1) ^ (r & 31)) << 2)) = make_float4(o8[4], o8[5], o8[6], o8[7]);
         }
-        store32(s_T[2], 8 * h + 4 * hh, v);
       }
     }
     __syncthreads();
     {
-      // channel-owner pass over the staged g0 tile: bias / fiber-weight column sums AND the gradient
-      // of the receiver projection, gPd[dst] += g0, reduced over runs of equal dst (the rows are
-      // dst-sorted) so that one red.add per (run, channel) reaches L2 instead of one per edge
-      float sb = 0.f, sf0 = 0.f, sf1 = 0.f, sf2 = 0.f, sf3 = 0.f;
-      float run = 0.f;
-      int cur = s_tgt[rh * 64];
-      float* gdc = p.gPsPd + 128 + cc;
-#pragma unroll 8
-      for (int rr = rh * 64; rr < rh * 64 + 64; ++rr) {
-        const float gv = tile_elem(s_T[2], rr, cc);
+      // row-cooperative pass (warp w: rows 16w..16w+15, lane l: channels 4l..4l+3): the gradient of the
+      // sender projection goes out as one coalesced 512 B red.add per edge row; the gradient of the
+      // receiver projection is reduced over runs of equal dst first (the rows are dst-sorted) so that one
+      // red.add per (run, channel) reaches L2; bias / fiber-weight column sums stay in registers
+      float4 run = make_float4(0.f, 0.f, 0.f, 0.f);
+      int cur = s_ij[warp * 16].y;
+#pragma unroll 4
+      for (int rr = warp * 16; rr < warp * 16 + 16; ++rr) {
+        const float4 gv = *reinterpret_cast<const float4*>(s_g0 + rr * 128 + ((lane ^ (rr & 31)) << 2));
+        const int2 ij = s_ij[rr];
         const float4 f = s_fib[rr];
-        const int t_ = s_tgt[rr];
-        if (t_ != cur) {
-          if (cur >= 0) atomicAdd(gdc + (size_t)cur * 256, run);
-          cur = t_;
-          run = 0.f;
+        if (ij.x >= 0) red_add_v4(p.gPsPd + (size_t)ij.x * 256 + 4 * lane, gv.x, gv.y, gv.z, gv.w);
+        if (ij.y != cur) {
+          if (cur >= 0) red_add_v4(p.gPsPd + (size_t)cur * 256 + 128 + 4 * lane, run.x, run.y, run.z, run.w);
+          cur = ij.y;
+          run = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        run += gv;
-        sb += gv;
-        sf0 += gv * f.x; sf1 += gv * f.y; sf2 += gv * f.z; sf3 += gv * f.w;
+        run.x += gv.x; run.y += gv.y; run.z += gv.z; run.w += gv.w;
+        acc_b0.x += gv.x; acc_b0.y += gv.y; acc_b0.z += gv.z; acc_b0.w += gv.w;
+        acc_fl[0].x += gv.x * f.x; acc_fl[0].y += gv.y * f.x; acc_fl[0].z += gv.z * f.x; acc_fl[0].w += gv.w * f.x;
+        acc_fl[1].x += gv.x * f.y; acc_fl[1].y += gv.y * f.y; acc_fl[1].z += gv.z * f.y; acc_fl[1].w += gv.w * f.y;
+        acc_fl[2].x += gv.x * f.z; acc_fl[2].y += gv.y * f.z; acc_fl[2].z += gv.z * f.z; acc_fl[2].w += gv.w * f.z;
+        acc_fl[3].x += gv.x * f.w; acc_fl[3].y += gv.y * f.w; acc_fl[3].z += gv.z * f.w; acc_fl[3].w += gv.w * f.w;
       }
-      if (cur >= 0) atomicAdd(gdc + (size_t)cur * 256, run);
-      acc_b[0] += sb;
-      acc_f[0] += sf0; acc_f[1] += sf1; acc_f[2] += sf2; acc_f[3] += sf3;
+      if (cur >= 0) red_add_v4(p.gPsPd + (size_t)cur * 256 + 128 + 4 * lane, run.x, run.y, run.z, run.w);
     }
-    __syncthreads();  // T2 / s_fib are rewritten by the next tile
+    __syncthreads();  // the staging tiles / row metadata are rewritten by the next tile
   }
 
   // ---- flush: weight-gradient accumulators (TMEM) and the per-thread bias / fiber partial sums
@@ -468,12 +461,19 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     }
   }
 #pragma unroll
-  for (int l = 0; l < 4; ++l) atomicAdd(p.gb[l] + cc, acc_b[l]);
+  for (int l = 1; l < 4; ++l) atomicAdd(p.gb[l] + cc, acc_b[l]);
   {
     const int ldw1 = 2 * kD + p.P + 1;
+    const float b0[4] = {acc_b0.x, acc_b0.y, acc_b0.z, acc_b0.w};
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (k <= p.P) atomicAdd(p.gW1 + (size_t)cc * ldw1 + k, acc_f[k]);
+    for (int c = 0; c < 4; ++c) {
+      atomicAdd(p.gb[0] + 4 * lane + c, b0[c]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float v = c == 0 ? acc_fl[k].x : (c == 1 ? acc_fl[k].y : (c == 2 ? acc_fl[k].z : acc_fl[k].w));
+        if (k <= p.P) atomicAdd(p.gW1 + (size_t)(4 * lane + c) * ldw1 + k, v);
+      }
+    }
   }
   fence_before_sync();
   __syncthreads();
