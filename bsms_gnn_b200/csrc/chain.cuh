@@ -58,6 +58,33 @@ __device__ __forceinline__ void coop_gather_a0(const float* __restrict__ PsPd, c
   }
 }
 
+// Row-cooperative load of NR contiguous-in-index rows (tile rows r_begin .. r_begin+NR-1 = global rows
+// row0 + r) into registers (lane l: channels 4l..4l+3 of each row; rows past `rows` read as zero), and
+// their conversion into a K-major SWIZZLE_128B bf16 operand tile.  Split so that the loads of the NEXT
+// tile can be in flight while the current tile computes.
+template <int NR>
+__device__ __forceinline__ void coop_rows_load(const float* __restrict__ X, int ld, long long row0, long long rows,
+                                               int r_begin, int lane, float4 (&v)[NR]) {
+#pragma unroll
+  for (int u = 0; u < NR; ++u) {
+    const long long row = row0 + r_begin + u;
+    v[u] = row < rows ? ld4(X + row * ld + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+template <int NR>
+__device__ __forceinline__ void coop_rows_store(uint8_t* tile, int r_begin, int lane, const float4 (&v)[NR]) {
+  const uint32_t col_off = (uint32_t)((lane >> 4) * 16384 + (lane & 1) * 8);
+  const int chunk7 = (lane >> 1) & 7;
+#pragma unroll
+  for (int u = 0; u < NR; ++u) {
+    const int r = r_begin + u;
+    uint2 pk;
+    pk.x = pack_bf16(v[u].x, v[u].y);
+    pk.y = pack_bf16(v[u].z, v[u].w);
+    *reinterpret_cast<uint2*>(tile + col_off + r * 128 + ((chunk7 ^ (r & 7)) << 4)) = pk;
+  }
+}
+
 struct PackList {
   const float* w[12];
   int ld[12];

@@ -17,6 +17,10 @@ int gmp_pack_blocks(const PackList& pl, int mode, uint8_t* out, cudaStream_t st)
 int lin_tc(int mode, const float* X0, int ldx0, const float* X1, int ldx1, int KB, int NB, const uint8_t* const* blocks,
            int b_mn, const float* bias, int relu, const float* mask, int ldmask, int accum, float* Y, int ldy,
            long long rows, int kind, cudaStream_t st);
+int lin_tc2(const float* X0, int ldx0, const float* X1, int ldx1, int KB, int NB, const uint8_t* const* blocks, int b_mn,
+            const float* bias, int relu, const float* mask, int ldmask, const float* add0, int ldadd0, const float* add1,
+            int ldadd1, float* Y0, int ldy0, float* Y1, int ldy1, float* ln_out, const float* res0, const float* res1,
+            long long rows, int kind, cudaStream_t st);
 int wgrad_tc_batch(const WgradParams* probs, int nprob, cudaStream_t st);
 WgradParams wgrad_problem(const float* G, int ldg, const float* X, int ldx, float* dW, int ldo, float* db, long long rows);
 int launch_ln_residual(const float* Yn, const float* x, const float* skip, float* out, long long rows, cudaStream_t st);
@@ -81,11 +85,39 @@ static NodeBufs carve_nodes(Arena& a, long long Rn) {
   return n;
 }
 
+// out != nullptr: the last layer also writes out = LN(Yn) + x (+ skip) (fused in the bf16 mode)
 static int forward_nodes(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos,
-                         int pos_batched, int B, int P, int mode, const NodeBufs& n, uint8_t* wpack, cudaStream_t st) {
+                         int pos_batched, int B, int P, int mode, const NodeBufs& n, uint8_t* wpack, const float* skip,
+                         float* out, cudaStream_t st) {
   const long long Rn = (long long)B * pl->n_nodes;
   const size_t bs = gmp_pack_stride(mode);
   auto blk = [&](int i) { return (const uint8_t*)(wpack + (size_t)i * bs); };
+  if (mode == BSMS_MODE_BF16) {
+    const int K = PK_NODE_FWD_GEMM;
+    {
+      const uint8_t* b[2] = {blk(BW1S), blk(BW1D)};  // Ps | Pd = x [W1s ; W1d]^T
+      TC_TRY(lin_tc2(x, kD, nullptr, 0, 1, 2, b, 0, reinterpret_cast<const float*>(wpack + kBiasSdOff), 0, nullptr, 0, nullptr,
+                     0, nullptr, 0, n.PsPd, 256, n.PsPd + 128, 256, nullptr, nullptr, nullptr, Rn, K, st));
+    }
+    BSMS_CUDA(cudaMemsetAsync(n.aggr, 0, (size_t)Rn * kD * sizeof(float), st));
+    TC_TRY(edge_chain_forward(pl, w, n.PsPd, pos, pos_batched, B, P, mode, wpack, n.aggr, nullptr, -1, st, true,
+                              wpack + kBiasPackOff));
+    {
+      const uint8_t* b[2] = {blk(BV1A), blk(BV1B)};  // N1 = relu([x | aggr] V1^T + c1)
+      TC_TRY(lin_tc2(x, kD, n.aggr, kD, 2, 1, b, 0, w->b_node[0], 1, nullptr, 0, nullptr, 0, nullptr, 0, n.N1, kD, nullptr, 0,
+                     nullptr, nullptr, nullptr, Rn, K, st));
+    }
+    const float* in[3] = {n.N1, n.N2, n.N3};
+    float* o[3] = {n.N2, n.N3, n.Yn};
+    const int bi[3] = {BV2, BV3, BV4};
+    for (int l = 0; l < 3; ++l) {
+      const uint8_t* b[1] = {blk(bi[l])};
+      const bool last = l == 2;
+      TC_TRY(lin_tc2(in[l], kD, nullptr, 0, 1, 1, b, 0, w->b_node[l + 1], last ? 0 : 1, nullptr, 0, nullptr, 0, nullptr, 0, o[l],
+                     kD, nullptr, 0, last ? out : nullptr, x, skip, Rn, K, st));
+    }
+    return BSMS_OK;
+  }
   {
     const uint8_t* b[2] = {blk(BW1S), blk(BW1D)};  // Ps | Pd = x [W1s ; W1d]^T
     TC_TRY(lin_tc(mode, x, kD, nullptr, 0, 1, 2, b, 0, reinterpret_cast<const float*>(wpack + kBiasSdOff), 0, nullptr, 0, 0,
@@ -110,6 +142,7 @@ static int forward_nodes(const bsms_level_plan* pl, const bsms_gmp_weights* w, c
     const uint8_t* b[1] = {blk(BV4)};
     TC_TRY(lin_tc(mode, n.N3, kD, nullptr, 0, 1, 1, b, 0, w->b_node[3], 0, nullptr, 0, 0, n.Yn, kD, Rn, PK_NODE_FWD_GEMM, st));
   }
+  if (out) return launch_ln_residual(n.Yn, x, skip, out, Rn, st);
   return BSMS_OK;
 }
 
@@ -126,8 +159,7 @@ int gmp_forward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const f
     return BSMS_EWORKSPACE;
   }
   TC_TRY(pack_all(w, P, mode, wpack, st));
-  TC_TRY(forward_nodes(pl, w, x, pos, pos_batched, B, P, mode, n, wpack, st));
-  return launch_ln_residual(n.Yn, x, skip, out, Rn, st);
+  return forward_nodes(pl, w, x, pos, pos_batched, B, P, mode, n, wpack, skip, out, st);
 }
 
 // bf16 backward: node MLP backward on tcgen05 GEMMs, fused edge backward, node-level layer-0 gradients
@@ -144,7 +176,7 @@ int gmp_backward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const 
   float* G2 = ar.take<float>(Rn * kD);
   float* G3 = ar.take<float>(Rn * kD);
   float* G4 = ar.take<float>(Rn * kD);
-  float* gcat = ar.take<float>(Rn * 256);
+  float* gcat = ar.take<float>(Rn * 256);  // only the first Rn*128 floats are used (g_aggr)
   float* gPsPd = ar.take<float>(Rn * 256);
   uint8_t* wpack = ar.take<uint8_t>(kScratchBytes);
   if (!ar.ok()) {
@@ -154,20 +186,19 @@ int gmp_backward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const 
   const size_t bs = gmp_pack_stride(mode);
   auto blk = [&](int i) { return (const uint8_t*)(wpack + (size_t)i * bs); };
   TC_TRY(pack_all(w, P, mode, wpack, st));
-  if (!saved) TC_TRY(forward_nodes(pl, w, x, pos, pos_batched, B, P, mode, n, wpack, st));
+  if (!saved) TC_TRY(forward_nodes(pl, w, x, pos, pos_batched, B, P, mode, n, wpack, nullptr, nullptr, st));
   // ---- node MLP backward: the data-gradient chain first, then ALL weight gradients in one launch
   TC_TRY(launch_ln_bwd_rows(n.Yn, g_out, kD, G1, Rn, st));  // G1 = gYn
   {
-    const uint8_t* b[1] = {blk(BV4)};
-    TC_TRY(lin_tc(mode, G1, kD, nullptr, 0, 1, 1, b, 1, nullptr, 0, n.N3, kD, 0, G2, kD, Rn, PK_DGRAD, st));
-  }
-  {
-    const uint8_t* b[1] = {blk(BV3)};
-    TC_TRY(lin_tc(mode, G2, kD, nullptr, 0, 1, 1, b, 1, nullptr, 0, n.N2, kD, 0, G3, kD, Rn, PK_DGRAD, st));
-  }
-  {
-    const uint8_t* b[1] = {blk(BV2)};
-    TC_TRY(lin_tc(mode, G3, kD, nullptr, 0, 1, 1, b, 1, nullptr, 0, n.N1, kD, 0, G4, kD, Rn, PK_DGRAD, st));
+    const float* gin[3] = {G1, G2, G3};
+    float* gout[3] = {G2, G3, G4};
+    const float* msk[3] = {n.N3, n.N2, n.N1};
+    const int bi[3] = {BV4, BV3, BV2};
+    for (int l = 0; l < 3; ++l) {
+      const uint8_t* b[1] = {blk(bi[l])};
+      TC_TRY(lin_tc2(gin[l], kD, nullptr, 0, 1, 1, b, 1, nullptr, 0, msk[l], kD, nullptr, 0, nullptr, 0, gout[l], kD, nullptr, 0,
+                     nullptr, nullptr, nullptr, Rn, PK_DGRAD, st));
+    }
   }
   {
     WgradParams pr[5] = {
@@ -179,19 +210,21 @@ int gmp_backward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const 
     TC_TRY(wgrad_tc_batch(pr, 5, st));
   }
   {
-    const uint8_t* b[2] = {blk(BV1A), blk(BV1B)};  // gcat = G4 V1 : [g_x part | g_aggr]
-    TC_TRY(lin_tc(mode, G4, kD, nullptr, 0, 1, 2, b, 1, nullptr, 0, nullptr, 0, 0, gcat, 256, Rn, PK_DGRAD, st));
+    // [g_x | g_aggr] = G4 V1: the x half leaves as g_x = g_out + ., the aggr half feeds the edge backward
+    const uint8_t* b[2] = {blk(BV1A), blk(BV1B)};
+    TC_TRY(lin_tc2(G4, kD, nullptr, 0, 1, 2, b, 1, nullptr, 0, nullptr, 0, g_out, kD, nullptr, 0, g_x, kD, gcat, kD, nullptr,
+                   nullptr, nullptr, Rn, PK_DGRAD, st));
   }
-  TC_TRY(launch_add_rows(g_out, gcat, 256, g_x, Rn, st));
   // ---- edge stage backward (fused) and the node-level gradients of the first edge layer
   if (Re > 0) {
     BSMS_CUDA(cudaMemsetAsync(gPsPd, 0, (size_t)Rn * 256 * sizeof(float), st));
-    TC_TRY(edge_chain_backward(pl, w, gr, n.PsPd, pos, pos_batched, B, P, wpack, gcat + 128, 256, gPsPd, st, true));
+    TC_TRY(edge_chain_backward(pl, w, gr, n.PsPd, pos, pos_batched, B, P, wpack, gcat, kD, gPsPd, st, true));
     WgradParams pr[2] = {wgrad_problem(gPsPd, 256, x, kD, gr->w_edge[0] + (P + 1), ldw1, nullptr, Rn),
                          wgrad_problem(gPsPd + 128, 256, x, kD, gr->w_edge[0] + (P + 1 + kD), ldw1, nullptr, Rn)};
     TC_TRY(wgrad_tc_batch(pr, 2, st));
     const uint8_t* b[2] = {blk(BW1S), blk(BW1D)};  // g_x += gPs W1s + gPd W1d
-    TC_TRY(lin_tc(mode, gPsPd, 256, gPsPd + 128, 256, 2, 1, b, 1, nullptr, 0, nullptr, 0, 1, g_x, kD, Rn, PK_DGRAD, st));
+    TC_TRY(lin_tc2(gPsPd, 256, gPsPd + 128, 256, 2, 1, b, 1, nullptr, 0, nullptr, 0, g_x, kD, nullptr, 0, g_x, kD, nullptr, 0,
+                   nullptr, nullptr, nullptr, Rn, PK_DGRAD, st));
   }
   return BSMS_OK;
 }

@@ -165,6 +165,178 @@ __global__ void __launch_bounds__(128, 2) k_lin(const LinParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
+// k_lin2 (bf16): the same contract as k_lin with every global access row-cooperative (one warp per
+// 512 B row: 4 L1 wavefronts per request instead of the 32 of a lane-per-row access pattern):
+//   load   : warp w brings rows 16w..16w+15 of the tile (lane l = channels 4l..4l+3), converts to bf16 and
+//            writes the K-major SWIZZLE_128B A tile in shared memory -> SS-form UMMA; K block 0 of the NEXT
+//            tile is prefetched into registers while the current tile's MMAs and epilogue run
+//   epilogue: thread (row, column half) reads its TMEM lane, applies bias / ReLU and stages fp32 into a
+//            row-swizzled shared-memory tile (aliases the A tiles, dead once the MMAs completed);
+//   store  : row-cooperative pass over the staged tile: ReLU-backward mask, addend, coalesced 512 B
+//            stores, and optionally the fused LayerNorm + residual of the node MLP's last layer
+//            (out = LN(y) + x [+ skip], reference src/ops/basic.py:18,98 and BSMS.py:102).
+// 256 threads; 64 KB (A / staging) + 32 KB per weight block: two CTAs per SM for the 1-block layers.
+struct Lin2Params {
+  const float* X[2];
+  int ldx[2];
+  int KB, NB;
+  const uint8_t* wblk[4];  // packed block of (nb, kb) at index nb*2+kb
+  int b_mn;
+  const float* bias;  // [NB*128] or null
+  int relu;
+  const float* mask;  // ReLU backward: keep where mask > 0 (column offset nb*128)
+  int ldmask;
+  const float* add[2];  // optional addend of output block nb
+  int ldadd[2];
+  float* Y[2];
+  int ldy[2];
+  float* ln_out;  // NB == 1: ln_out = LN(y) + res0 (+ res1), rows of 128
+  const float* res0;
+  const float* res1;
+  long long rows;
+  int ntiles;
+};
+
+__global__ void __launch_bounds__(256, 2) k_lin2(const Lin2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t idesc = make_idesc(1, 128, 128, 0, p.b_mn ? 1u : 0u);
+  const uint32_t s0 = smem_u32(smem_raw);
+  const uint32_t sbase = (s0 + 1023u) & ~1023u;
+  uint8_t* sp = smem_raw + (sbase - s0);
+  const int nblk = p.KB * p.NB;
+  // [A tiles / fp32 staging: 64 KB][weight blocks: nblk x 32 KB][bias 256 floats][barriers]
+  uint8_t* s_A = sp;
+  float* s_stage = reinterpret_cast<float*>(sp);
+  const uint32_t a_addr = sbase, w_addr = sbase + 2 * kWBlk;
+  float* s_bias = reinterpret_cast<float*>(sp + 2 * kWBlk + nblk * kWBlk);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 256);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar_w = smem_u32(&s_bar[0]), bar_m = smem_u32(&s_bar[1]);
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_m, 1);
+    fence_mbar_init();
+  }
+  const uint32_t ncols = p.NB == 2 ? 256u : 128u;
+  if (warp == 0) tmem_alloc(smem_u32(s_tmem), ncols);
+  for (int i = tid; i < 128 * p.NB; i += 256) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+  if (tid == 0) {
+    mbar_expect_tx(bar_w, nblk * kWBlk);
+    for (int nb = 0; nb < p.NB; ++nb)
+      for (int kb = 0; kb < p.KB; ++kb)
+        bulk_g2s(w_addr + (nb * p.KB + kb) * kWBlk, p.wblk[nb * 2 + kb], kWBlk, bar_w);
+  }
+  const int q = warp & 3, h = warp >> 2, r = q * 32 + lane;
+  const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+  uint32_t phase = 0;
+  bool weights_ready = false;
+  float4 pre[16];  // K block 0 of the next tile, rows 16*warp .. 16*warp+15
+  if ((int)blockIdx.x < p.ntiles) coop_rows_load<16>(p.X[0], p.ldx[0], (long long)blockIdx.x * 128, p.rows, warp * 16, lane, pre);
+
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    const long long row0 = (long long)tile * 128;
+    coop_rows_store<16>(s_A, warp * 16, lane, pre);
+    if (p.KB == 2) {
+      float4 v1[16];
+      coop_rows_load<16>(p.X[1], p.ldx[1], row0, p.rows, warp * 16, lane, v1);
+      coop_rows_store<16>(s_A + kWBlk, warp * 16, lane, v1);
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      if (!weights_ready) {
+        mbar_wait(bar_w, 0);
+        weights_ready = true;
+      }
+      fence_after_sync();
+      for (int nb = 0; nb < p.NB; ++nb)
+        for (int kb = 0; kb < p.KB; ++kb) {
+          const uint32_t wb = w_addr + (nb * p.KB + kb) * kWBlk;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t ad = smem_desc_sw128(a_addr + kb * kWBlk + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
+            const uint32_t off = p.b_mn ? ks * 2048 : (ks >> 2) * 16384 + (ks & 3) * 32;
+            const uint64_t bd = smem_desc_sw128(wb + off, p.b_mn ? 16384 : 16, 1024);
+            mma_ss(tmem_base + nb * 128, ad, bd, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+      mma_commit(bar_m);
+    }
+    {
+      const int next = tile + gridDim.x;
+      if (next < p.ntiles) coop_rows_load<16>(p.X[0], p.ldx[0], (long long)next * 128, p.rows, warp * 16, lane, pre);
+    }
+    mbar_wait(bar_m, phase);
+    phase ^= 1;
+    fence_after_sync();
+    for (int nb = 0; nb < p.NB; ++nb) {
+      // ---- TMEM -> (+bias, ReLU) -> fp32 staging; 16-byte chunks XOR-swizzled by row (conflict free both ways)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t rr_[32];
+        tmem_ld32(tmem_base + nb * 128 + lane_off + 64 * h + 32 * hh, rr_);
+        wait_ld();
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float x = __uint_as_float(rr_[q4 * 4 + e]) + s_bias[nb * 128 + 64 * h + 32 * hh + q4 * 4 + e];
+            o[e] = p.relu ? fmaxf(x, 0.f) : x;
+          }
+          const int c4 = 16 * h + 8 * hh + q4;
+          *reinterpret_cast<float4*>(s_stage + r * 128 + ((c4 ^ (r & 31)) << 2)) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      __syncthreads();
+      // ---- row-cooperative store pass
+      const float* mk = p.mask ? p.mask + nb * 128 + 4 * lane : nullptr;
+      const float* ad = p.add[nb] ? p.add[nb] + 4 * lane : nullptr;
+      float* yo = p.Y[nb] + 4 * lane;
+#pragma unroll 4
+      for (int rr = warp * 16; rr < warp * 16 + 16; ++rr) {
+        const long long row = row0 + rr;
+        if (row < p.rows) {
+          float4 v = *reinterpret_cast<const float4*>(s_stage + rr * 128 + ((lane ^ (rr & 31)) << 2));
+          if (mk) {
+            const float4 m = ld4(mk + row * p.ldmask);
+            v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+          }
+          if (ad) {
+            const float4 a = ld4(ad + row * p.ldadd[nb]);
+            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+          }
+          st4(yo + row * p.ldy[nb], v);
+          if (p.ln_out) {
+            const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.f / 128.f);
+            const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+            const float var = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.f / 128.f);
+            const float rstd = 1.f / sqrtf(var + 1e-5f);
+            float4 o = ld4(p.res0 + row * 128 + 4 * lane);
+            o.x += dx * rstd; o.y += dy * rstd; o.z += dz * rstd; o.w += dw * rstd;
+            if (p.res1) {
+              const float4 s = ld4(p.res1 + row * 128 + 4 * lane);
+              o.x += s.x; o.y += s.y; o.z += s.z; o.w += s.w;
+            }
+            st4(p.ln_out + row * 128 + 4 * lane, o);
+          }
+        }
+      }
+      __syncthreads();  // the staging tile is rewritten by the next block / the next tile's A tiles
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, ncols);
+}
+
+// ------------------------------------------------------------------------------------------
 // several independent weight-gradient problems in one launch (CTA c works on problem c / ctas_per_prob)
 struct WgradBatch {
   WgradParams prob[6];
@@ -200,7 +372,6 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradBatch batch) {
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *s_tmem;
-  const int r = tid >> 1, h = tid & 1;  // row of the tile, channel half
   const int cc = tid & 127, rh = tid >> 7;
   float acc_b = 0.f;
   uint32_t ph[2] = {0u, 0u};
@@ -212,23 +383,19 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradBatch batch) {
       mbar_wait(s ? bar1 : bar0, ph[s]);
       ph[s] ^= 1;
     }
-    const long long row = (long long)tile * 128 + r;
-    const bool valid = row < p.rows;
     uint8_t* tg = sp + (2 * s) * kWBlk;
     uint8_t* tx = sp + (2 * s + 1) * kWBlk;
-    const float* gr = p.G + row * p.ldg + 64 * h;
-    const float* xr = p.X + row * p.ldx + 64 * h;
+    // row-cooperative loads: warp w brings rows 16w..16w+15 of both tiles as coalesced 512 B rows
+    {
+      const long long row0 = (long long)tile * 128;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 a0 = valid ? ld4(gr + 8 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 a1 = valid ? ld4(gr + 8 * j + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      uint4 u;
-      u.x = pack_bf16(a0.x, a0.y); u.y = pack_bf16(a0.z, a0.w); u.z = pack_bf16(a1.x, a1.y); u.w = pack_bf16(a1.z, a1.w);
-      *reinterpret_cast<uint4*>(tg + t_off(r, 8 * h + j)) = u;
-      float4 b0 = valid ? ld4(xr + 8 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 b1 = valid ? ld4(xr + 8 * j + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      u.x = pack_bf16(b0.x, b0.y); u.y = pack_bf16(b0.z, b0.w); u.z = pack_bf16(b1.x, b1.y); u.w = pack_bf16(b1.z, b1.w);
-      *reinterpret_cast<uint4*>(tx + t_off(r, 8 * h + j)) = u;
+      for (int half = 0; half < 2; ++half) {
+        float4 vg[8], vx[8];
+        coop_rows_load<8>(p.G, p.ldg, row0, p.rows, warp * 16 + 8 * half, lane, vg);
+        coop_rows_load<8>(p.X, p.ldx, row0, p.rows, warp * 16 + 8 * half, lane, vx);
+        coop_rows_store<8>(tg, warp * 16 + 8 * half, lane, vg);
+        coop_rows_store<8>(tx, warp * 16 + 8 * half, lane, vx);
+      }
     }
     fence_proxy_async();
     fence_before_sync();
@@ -342,6 +509,46 @@ int lin_tc(int mode, const float* X0, int ldx0, const float* X1, int ldx1, int K
     BSMS_CUDA(cudaFuncSetAttribute(k_lin<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_lin<1><<<grid, 128, smem, st>>>(p);
   }
+  BSMS_LAUNCHED();
+  return BSMS_OK;
+}
+
+
+// bf16 layer with row-cooperative I/O (k_lin2).  add0/add1: optional addends of the two output blocks; Y0/Y1
+// separate destinations; ln_out: fused LayerNorm + residual (NB == 1).
+int lin_tc2(const float* X0, int ldx0, const float* X1, int ldx1, int KB, int NB, const uint8_t* const* blocks, int b_mn,
+            const float* bias, int relu, const float* mask, int ldmask, const float* add0, int ldadd0, const float* add1,
+            int ldadd1, float* Y0, int ldy0, float* Y1, int ldy1, float* ln_out, const float* res0, const float* res1,
+            long long rows, int kind, cudaStream_t st) {
+  if (rows == 0) return BSMS_OK;
+  Lin2Params p;
+  p.X[0] = X0; p.X[1] = X1;
+  p.ldx[0] = ldx0; p.ldx[1] = ldx1;
+  p.KB = KB; p.NB = NB;
+  for (int i = 0; i < 4; ++i) p.wblk[i] = nullptr;
+  for (int nb = 0; nb < NB; ++nb)
+    for (int kb = 0; kb < KB; ++kb) p.wblk[nb * 2 + kb] = blocks[nb * KB + kb];
+  p.b_mn = b_mn;
+  p.bias = bias;
+  p.relu = relu;
+  p.mask = mask;
+  p.ldmask = ldmask;
+  p.add[0] = add0; p.add[1] = add1;
+  p.ldadd[0] = ldadd0; p.ldadd[1] = ldadd1;
+  p.Y[0] = Y0; p.Y[1] = Y1;
+  p.ldy[0] = ldy0; p.ldy[1] = ldy1;
+  p.ln_out = ln_out;
+  p.res0 = res0;
+  p.res1 = res1;
+  p.rows = rows;
+  p.ntiles = ceil_div(rows, 128);
+  const int nblk = KB * NB;
+  const int per_sm = nblk == 1 ? 2 : 1;
+  const int grid = std::min(per_sm * sm_count(), p.ntiles);
+  const size_t smem = 1024 + (2 + nblk) * kWBlk + 1024 + 64;
+  BSMS_CUDA(cudaFuncSetAttribute(k_lin2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 + 4 * kWBlk + 1024 + 64)));
+  ProfScope ps_(kind, st);
+  k_lin2<<<grid, 256, smem, st>>>(p);
   BSMS_LAUNCHED();
   return BSMS_OK;
 }
