@@ -324,46 +324,92 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
         const float var = fmaxf(ssq * (1.f / 128.f) - mean_d * mean_d, 0.f);
         const float rstd = 1.f / sqrtf(var + 1e-5f);
         const float mean = shift + mean_d;
-        const int ch = lane % CH, grp = lane / CH;
-        const uint32_t gm = (startmask >> (grp * RPG)) | 1u;
+        if constexpr (COOP) {
+          // Pass 2, row-cooperative: the warp's 32 normalised rows go through its private 8 KB of the
+          // (dead) a0 tile, 64 channels at a time ([32][64] fp32, 16-byte chunks XOR-swizzled by row);
+          // then each half-warp walks 16 of the dst-sorted rows with lane = 4 channels and flushes every
+          // finished run of equal destination with ONE 16-byte red.add per lane (256 B per half-warp).
+          float* wstage = reinterpret_cast<float*>(s_a0 + wg * kWBlk + q * 8192);
+          const int l16 = lane & 15, hw = lane >> 4;
 #pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(d_tmem + lane_off + c0, r);
-          wait_ld();
-          if (p.dbg && p.dbg_stage == 3 && valid) {
-#pragma unroll
-            for (int t = 0; t < 32; ++t)
-              p.dbg[row * 128 + c0 + t] = BIAS_MMA ? __uint_as_float(r[t]) : fmaf(__uint_as_float(r[t]), OUT_SCALE, bias[c0 + t]);
-          }
-#pragma unroll
-          for (int sub = 0; sub < 32; sub += CH) {
+          for (int half = 0; half < 2; ++half) {
             __syncwarp();
 #pragma unroll
-            for (int t = 0; t < CH; ++t) {
-              const float y = BIAS_MMA ? __uint_as_float(r[sub + t])
-                                       : fmaf(__uint_as_float(r[sub + t]), OUT_SCALE, bias[c0 + sub + t]);
-              stage[lane * (CH + 1) + t] = (y - mean) * rstd;
-            }
-            __syncwarp();
-            // lanes own channels now and walk the rows of their group; a set bit in gm starts a new
-            // destination: flush the finished run with one red.add per channel (128 B per warp)
-            float* dstc = p.aggr + c0 + sub + ch;
-            const float* col = stage + (grp * RPG) * (CH + 1) + ch;
-            float acc = col[0];
-            int cur = tgt[grp * RPG];
+            for (int cc = 0; cc < 2; ++cc) {
+              uint32_t r[32];
+              tmem_ld32(d_tmem + lane_off + 64 * half + 32 * cc, r);
+              wait_ld();
+              if (p.dbg && p.dbg_stage == 3 && valid) {
 #pragma unroll
-            for (int rl = 1; rl < RPG; ++rl) {
-              const float m = col[rl * (CH + 1)];
-              if ((gm >> rl) & 1u) {
-                if (cur >= 0) atomicAdd(dstc + (size_t)cur * 128, acc);
-                cur = tgt[grp * RPG + rl];
-                acc = m;
-              } else {
-                acc += m;
+                for (int t = 0; t < 32; ++t) p.dbg[row * 128 + 64 * half + 32 * cc + t] = __uint_as_float(r[t]);
+              }
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                const float4 o = make_float4((__uint_as_float(r[4 * q4 + 0]) - mean) * rstd, (__uint_as_float(r[4 * q4 + 1]) - mean) * rstd,
+                                             (__uint_as_float(r[4 * q4 + 2]) - mean) * rstd, (__uint_as_float(r[4 * q4 + 3]) - mean) * rstd);
+                *reinterpret_cast<float4*>(wstage + lane * 64 + (((8 * cc + q4) ^ (lane & 15)) << 2)) = o;
               }
             }
-            if (cur >= 0) atomicAdd(dstc + (size_t)cur * 128, acc);
+            __syncwarp();
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            int cur = -1;
+            float* dstc = p.aggr + 64 * half + 4 * l16;
+#pragma unroll 4
+            for (int k = 0; k < 16; ++k) {
+              const int rr = 16 * hw + k;
+              const float4 m = *reinterpret_cast<const float4*>(wstage + rr * 64 + ((l16 ^ k) << 2));
+              if (k == 0 || ((startmask >> rr) & 1u)) {
+                if (cur >= 0) red_add_v4(dstc + (size_t)cur * 128, acc.x, acc.y, acc.z, acc.w);
+                cur = tgt[rr];
+                acc = m;
+              } else {
+                acc.x += m.x; acc.y += m.y; acc.z += m.z; acc.w += m.w;
+              }
+            }
+            if (cur >= 0) red_add_v4(dstc + (size_t)cur * 128, acc.x, acc.y, acc.z, acc.w);
+          }
+        } else {
+          const int ch = lane % CH, grp = lane / CH;
+          const uint32_t gm = (startmask >> (grp * RPG)) | 1u;
+  #pragma unroll 1
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(d_tmem + lane_off + c0, r);
+            wait_ld();
+            if (p.dbg && p.dbg_stage == 3 && valid) {
+  #pragma unroll
+              for (int t = 0; t < 32; ++t)
+                p.dbg[row * 128 + c0 + t] = BIAS_MMA ? __uint_as_float(r[t]) : fmaf(__uint_as_float(r[t]), OUT_SCALE, bias[c0 + t]);
+            }
+  #pragma unroll
+            for (int sub = 0; sub < 32; sub += CH) {
+              __syncwarp();
+  #pragma unroll
+              for (int t = 0; t < CH; ++t) {
+                const float y = BIAS_MMA ? __uint_as_float(r[sub + t])
+                                         : fmaf(__uint_as_float(r[sub + t]), OUT_SCALE, bias[c0 + sub + t]);
+                stage[lane * (CH + 1) + t] = (y - mean) * rstd;
+              }
+              __syncwarp();
+              // lanes own channels now and walk the rows of their group; a set bit in gm starts a new
+              // destination: flush the finished run with one red.add per channel (128 B per warp)
+              float* dstc = p.aggr + c0 + sub + ch;
+              const float* col = stage + (grp * RPG) * (CH + 1) + ch;
+              float acc = col[0];
+              int cur = tgt[grp * RPG];
+  #pragma unroll
+              for (int rl = 1; rl < RPG; ++rl) {
+                const float m = col[rl * (CH + 1)];
+                if ((gm >> rl) & 1u) {
+                  if (cur >= 0) atomicAdd(dstc + (size_t)cur * 128, acc);
+                  cur = tgt[grp * RPG + rl];
+                  acc = m;
+                } else {
+                  acc += m;
+                }
+              }
+              if (cur >= 0) atomicAdd(dstc + (size_t)cur * 128, acc);
+            }
           }
         }
         __syncwarp();

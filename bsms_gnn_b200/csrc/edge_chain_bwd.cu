@@ -7,9 +7,10 @@
 //   a0 = relu(Ps[src]+Pd[dst]+b1+F fiber)            row-cooperative gather (one warp per 512 B row) -> T0 (bf16 smem tile)
 //   a1 = relu(a0 W2^T + b2)                           UMMA  D=T0 x W2   -> T1, m1
 //   a2 = relu(a1 W3^T + b3)                           UMMA  D=T1 x W3   -> T2, m2
-//   y  = a2 W4^T + b4 ; gy = LN'(y) * g_aggr[dst]     UMMA  D=T2 x W4   -> T0 (a0 is re-gathered later)
-//   dW4 += gy^T a2 ; g2 = (gy W4) . m2                UMMA  wgrad(T0,T2), dgrad D=T0 x W4(MN)  -> T2
-//   dW3 += g2^T a1 ; g1 = (g2 W3) . m1                UMMA  wgrad(T2,T1), dgrad D=T2 x W3(MN)  -> T1 ; a0 -> T0
+//   y  = a2 W4^T + b4 ; gy = LN'(y) * g_aggr[dst]     UMMA  D=T2 x W4   -> the W2 slot (W2 is idle until the last dgrad;
+//                                                     cp.async.bulk brings it back from L2 once gy is consumed)
+//   dW4 += gy^T a2 ; g2 = (gy W4) . m2                UMMA  wgrad(gy,T2), dgrad D=gy x W4(MN)  -> T2
+//   dW3 += g2^T a1 ; g1 = (g2 W3) . m1                UMMA  wgrad(T2,T1), dgrad D=T2 x W3(MN)  -> T1
 //   dW2 += g1^T a0 ; g0 = (g1 W2) . [a0>0]            UMMA  wgrad(T1,T0), dgrad D=T1 x W2(MN)  -> fp32 staging over T1|T2
 //   gPs[src] += g0 (one coalesced 512 B red.add.v4 per row) ; gPd[dst] += run sums of g0 ; gF += g0^T fiber ; gb* += column sums
 // The three weight-gradient accumulators (3 x 128 TMEM columns) stay resident in tensor memory for
@@ -91,17 +92,18 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
   float4* s_x = s_fib + 128;                                 // [2][128] LayerNorm partial sums
   int2* s_ij = reinterpret_cast<int2*>(s_x + 256);           // [128] (b*N+src, b*N+dst) of each tile row, -1 past the end
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_ij + 128);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 3);
   const uint32_t aW[3] = {sbase, sbase + kWBlk, sbase + 2 * kWBlk};
   const uint32_t aT[3] = {sbase + 3 * kWBlk, sbase + 4 * kWBlk, sbase + 5 * kWBlk};
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, h = warp >> 2, r = q * 32 + lane;
-  const uint32_t bar_w = smem_u32(&s_bar[0]), bar_m = smem_u32(&s_bar[1]);
+  const uint32_t bar_w = smem_u32(&s_bar[0]), bar_m = smem_u32(&s_bar[1]), bar_r = smem_u32(&s_bar[2]);
 
   if (tid == 0) {
     mbar_init(bar_w, 1);
     mbar_init(bar_m, 1);
+    mbar_init(bar_r, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
@@ -130,11 +132,14 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
   const uint32_t d_tmem = tmem_base;  // D: cols [0,128); dW2/dW3/dW4: cols [128,256), [256,384), [384,512)
   const uint32_t lane_off = (uint32_t)(q * 32) << 16;
   const uint32_t d_mine = d_tmem + lane_off + 64 * h;
-  uint32_t phase = 0;
+  uint32_t phase = 0, phase_r = 0;
+  uint8_t* s_gy = sp;  // the W2 slot: W2 is idle between the first recompute GEMM and the last data-gradient GEMM,
+                       // so gy lives there meanwhile and W2 is brought back by cp.async.bulk (32 KB from L2 per tile)
   uint32_t wacc = 0;  // weight-gradient accumulators hold something
   // persistent per-thread partial sums for the bias / fiber-weight gradients (channel cc, row half rh)
-  const int cc = tid & 127, rh = tid >> 7;
-  float acc_b[4] = {0.f, 0.f, 0.f, 0.f};  // [0] unused: gb1 / gF are accumulated per lane below
+  float4 acc_b[4];  // bias-gradient partial sums of this lane's 4 channels; [0] unused (acc_b0 below)
+#pragma unroll
+  for (int l = 0; l < 4; ++l) acc_b[l] = make_float4(0.f, 0.f, 0.f, 0.f);
   // row-cooperative passes: lane l owns channels 4l..4l+3
   float4 acc_b0 = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 acc_fl[4];  // [fiber component k] x 4 channels
@@ -173,14 +178,20 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       mma_ss(dw_tmem, ad, bd, IDESC_MM, (wacc | ks) != 0);
     }
   };
-  // column sums of a gradient tile (bias gradient) by channel-owner threads; overlaps the MMAs
-  auto colsum = [&](const uint8_t* tile, float& acc) {
-    float s = 0.f;
+  // column sums of a gradient tile (bias gradient), row-cooperative: warp w sums rows 16w..16w+15, lane l
+  // owns channels 4l..4l+3 (one 8-byte shared load per row); overlaps the MMAs
+  auto colsum = [&](const uint8_t* tile, float4& acc) {
+    const uint8_t* base = tile + (lane >> 4) * 16384 + (lane & 1) * 8;
+    const int chunk7 = (lane >> 1) & 7;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
-    for (int rr = rh * 64; rr < rh * 64 + 64; ++rr) s += tile_elem(tile, rr, cc);
-    acc += s;
+    for (int rr = warp * 16; rr < warp * 16 + 16; ++rr) {
+      const uint2 u = *reinterpret_cast<const uint2*>(base + rr * 128 + ((chunk7 ^ (rr & 7)) << 4));
+      s.x += __uint_as_float(u.x << 16); s.y += __uint_as_float(u.x & 0xFFFF0000u);
+      s.z += __uint_as_float(u.y << 16); s.w += __uint_as_float(u.y & 0xFFFF0000u);
+    }
+    acc.x += s.x; acc.y += s.y; acc.z += s.z; acc.w += s.w;
   };
-
   auto gather_a0 = [&]() {
     float4 Fl[4];  // fiber coefficients of this lane's 4 channels
 #pragma unroll
@@ -356,18 +367,23 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
           uint4 u;
           u.x = pack_bf16(o8[0], o8[1]); u.y = pack_bf16(o8[2], o8[3]);
           u.z = pack_bf16(o8[4], o8[5]); u.w = pack_bf16(o8[6], o8[7]);
-          *reinterpret_cast<uint4*>(s_T[0] + tile_off(r, 8 * h + 4 * hh + jj)) = u;
+          *reinterpret_cast<uint4*>(s_gy + tile_off(r, 8 * h + 4 * hh + jj)) = u;
         }
       }
     }
     sync_all();
     if (tid == 0) {
-      issue_wgrad(tmem_base + 384, aT[0], aT[2]);  // dW4 += gy^T a2
-      issue_gemm(aT[0], aW[2], true);              // D = gy W4
+      issue_wgrad(tmem_base + 384, aW[0], aT[2]);  // dW4 += gy^T a2
+      issue_gemm(aW[0], aW[2], true);              // D = gy W4
       mma_commit(bar_m);
     }
-    colsum(s_T[0], acc_b[3]);
+    colsum(s_gy, acc_b[3]);
+    __syncthreads();  // every warp is done reading gy through the generic proxy
     wait_mma();
+    if (tid == 0) {  // gy is dead: bring W2 back into its slot
+      mbar_expect_tx(bar_r, kWBlk);
+      bulk_g2s(aW[0], p.wpack, kWBlk, bar_r);
+    }
     grad_epilogue(m2, s_T[2]);  // g2 -> T2
     sync_all();
     if (tid == 0) {
@@ -376,17 +392,17 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       mma_commit(bar_m);
     }
     colsum(s_T[2], acc_b[2]);
-    // a0 again (T0 was reused for gy); the generic-proxy writes are fenced by the next sync_all
-    gather_a0();
     wait_mma();
     grad_epilogue(m1, s_T[1]);  // g1 -> T1
     sync_all();
     if (tid == 0) {
+      mbar_wait(bar_r, phase_r);                   // W2 is back
       issue_wgrad(tmem_base + 128, aT[1], aT[0]);  // dW2 += g1^T a0
       issue_gemm(aT[1], aW[0], true);              // D = g1 W2
       mma_commit(bar_m);
       wacc = 1;
     }
+    phase_r ^= 1;
     colsum(s_T[1], acc_b[1]);
     wait_mma();
     // ---- g0 = D . [a0 > 0] (mask re-derived from the a0 tile) -> fp32 staging over T1|T2, 16-byte
@@ -461,7 +477,12 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     }
   }
 #pragma unroll
-  for (int l = 1; l < 4; ++l) atomicAdd(p.gb[l] + cc, acc_b[l]);
+  for (int l = 1; l < 4; ++l) {
+    atomicAdd(p.gb[l] + 4 * lane + 0, acc_b[l].x);
+    atomicAdd(p.gb[l] + 4 * lane + 1, acc_b[l].y);
+    atomicAdd(p.gb[l] + 4 * lane + 2, acc_b[l].z);
+    atomicAdd(p.gb[l] + 4 * lane + 3, acc_b[l].w);
+  }
   {
     const int ldw1 = 2 * kD + p.P + 1;
     const float b0[4] = {acc_b0.x, acc_b0.y, acc_b0.z, acc_b0.w};
