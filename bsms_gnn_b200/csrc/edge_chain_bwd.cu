@@ -501,7 +501,8 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-size_t edge_chain_bwd_smem() { return 1024 + 6 * kWBlk + 512 * 4 + 128 * 16 * 2 + 256 * 16 + 128 * 4 + 2 * 8 + 16; }
+// alignment slack + 3 weight slots + 3 tiles + s_bias[512] + s_F[128] + s_fib[128] + s_x[2][128] + s_ij[128] + 3 barriers + TMEM address
+size_t edge_chain_bwd_smem() { return 1024 + 6 * kWBlk + 512 * 4 + 128 * 16 * 2 + 256 * 16 + 128 * 8 + 3 * 8 + 16; }
 
 // Fused bf16 backward of the edge stage.  gPsPd must be zero-filled; gW/gb/gW1 are accumulated into.
 int edge_chain_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const bsms_gmp_grads* gr, const float* PsPd,
