@@ -20,6 +20,8 @@
 // fp32 bias added in the epilogue.
 //
 // PsPd holds the per-node projections with b1 already folded into the Pd half.
+#include <stdlib.h>
+
 #include "chain.cuh"
 
 namespace bsms {
@@ -43,6 +45,7 @@ struct EdgeChainParams {
   int ntiles;
   float* dbg;
   int dbg_stage;
+  unsigned long long* prof;  // optional [16] per-phase cycle counters of warpgroup 0 (BSMS_PHASE_PROF=1)
 };
 
 // b2..b4 -> three 16 KB blocks in the K-major SW128 image: element (n, k=0) = bias[n], rest 0
@@ -106,6 +109,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
   int* s_tgt = reinterpret_cast<int*>(s_stage + (COOP ? 0 : 8 * 32 * (CH + 1)));
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tgt + 256);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 3);
+  unsigned long long* s_prof = reinterpret_cast<unsigned long long*>(s_tmem + 2);  // [16]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wg = warp >> 2, tw = tid & 127, q = warp & 3;
@@ -157,7 +161,20 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
 #pragma unroll
   for (int c = 0; c < 4; ++c) Fl[c] = s_F[4 * lane + c];
 
+  long long tprev = 0;
+  if (p.prof && tid == 0) {
+    for (int k = 0; k < 16; ++k) s_prof[k] = 0ull;
+    tprev = clock64();
+  }
+  auto mark = [&](int k) {
+    if (p.prof && tid == 0) {
+      const long long t = clock64();
+      s_prof[k] += (unsigned long long)(t - tprev);
+      tprev = t;
+    }
+  };
   for (int tile = blockIdx.x * 2 + wg; tile < p.ntiles; tile += gridDim.x * 2) {
+    mark(0);
     const long long row = (long long)tile * 128 + tw;
     const bool valid = row < p.rows;
     int b = 0, i = 0, j = 0;
@@ -249,12 +266,14 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
         }
       }
     }
+    mark(1);
     // ---- three UMMA layers
 #pragma unroll 1
     for (int layer = 0; layer < 3; ++layer) {
       wait_st();
       fence_before_sync();
       bar_sync(1 + wg, 128);
+      mark(2 + 3 * layer);
       if (tw == 0) {
         if (!weights_ready) {
           mbar_wait(bar_w, 0);
@@ -283,6 +302,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
       mbar_wait(bar_m, phase);
       phase ^= 1;
       fence_after_sync();
+      mark(3 + 3 * layer);
       const float* bias = s_bias + layer * 128;
       if (layer < 2) {
 #pragma unroll 1
@@ -302,6 +322,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
           }
           store_act32<NSPLIT>(a_tmem + lane_off, c0, v);
         }
+        mark(4 + 3 * layer);
       } else {
         // ---- final: LayerNorm over the row.  Pass 1: shifted sums (shift = first element, so the
         //      one-pass variance has no cancellation); pass 2: normalise + segmented reduce by dst.
@@ -324,6 +345,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
         const float var = fmaxf(ssq * (1.f / 128.f) - mean_d * mean_d, 0.f);
         const float rstd = 1.f / sqrtf(var + 1e-5f);
         const float mean = shift + mean_d;
+        mark(10);
         if constexpr (COOP) {
           // Pass 2, row-cooperative: the warp's 32 normalised rows go through its private 8 KB of the
           // (dead) a0 tile, 64 channels at a time ([32][64] fp32, 16-byte chunks XOR-swizzled by row);
@@ -416,6 +438,9 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
       }
     }
   }
+  mark(11);
+  if (p.prof && tid == 0)
+    for (int k = 0; k < 16; ++k) atomicAdd(p.prof + k, s_prof[k]);
   // teardown
   fence_before_sync();
   __syncthreads();
@@ -425,7 +450,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
 template <int NSPLIT, int CH>
 static size_t edge_chain_smem() {
   return 1024 + 3 * NSPLIT * kWBlk + (NSPLIT == 1 ? 3 * kBiasBlk + 2 * kWBlk : 0) + 384 * 4 + 128 * 16 + 256 * 16 + 256 * 8 +
-         (NSPLIT == 1 ? 0 : 8 * 32 * (CH + 1) * 4) + 256 * 4 + 3 * 8 + 16;
+         (NSPLIT == 1 ? 0 : 8 * 32 * (CH + 1) * 4) + 256 * 4 + 3 * 8 + 16 + 128;
 }
 
 size_t edge_chain_pack_bytes(int mode) { return (size_t)3 * (mode == BSMS_MODE_FP16X3 ? 2 : 1) * kWBlk + 3 * kBiasBlk; }
@@ -462,6 +487,25 @@ int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, con
   p.ntiles = ceil_div(rows, 128);
   p.dbg = dbg;
   p.dbg_stage = dbg_stage;
+  static const bool phase_prof = getenv("BSMS_PHASE_PROF") != nullptr;
+  static unsigned long long* d_prof = nullptr;
+  p.prof = nullptr;
+  if (phase_prof) {
+    if (!d_prof) BSMS_CUDA(cudaMalloc(&d_prof, 16 * sizeof(unsigned long long)));
+    BSMS_CUDA(cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), st));
+    p.prof = d_prof;
+  }
+  auto report = [&]() -> int {
+    if (!phase_prof) return BSMS_OK;
+    unsigned long long h[16];
+    BSMS_CUDA(cudaMemcpyAsync(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost, st));
+    BSMS_CUDA(cudaStreamSynchronize(st));
+    const unsigned long long nt = (unsigned long long)((p.ntiles + 1) / 2);  // tiles seen by warpgroup 0
+    fprintf(stderr, "[fwd phases] tiles %d:", p.ntiles);
+    for (int k = 0; k < 12; ++k) fprintf(stderr, " %llu", h[k] / nt);
+    fprintf(stderr, "\n");
+    return BSMS_OK;
+  };
   int dev = 0, sms = 148;
   BSMS_CUDA(cudaGetDevice(&dev));
   BSMS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -483,6 +527,7 @@ int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, con
     ProfScope ps_(PK_EDGE_CHAIN, st);
     kern<<<grid, 256, smem, st>>>(p);
     BSMS_LAUNCHED();
+    if (report() != BSMS_OK) return BSMS_ECUDA;
   } else {
     if (!prepacked) {
       ProfScope ps_(PK_OTHER, st);

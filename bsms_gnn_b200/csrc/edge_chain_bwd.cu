@@ -19,6 +19,8 @@
 // K-major operands (forward / data-gradient GEMMs) and as MN-major operands (weight-gradient
 // GEMMs) by re-describing the same bytes.  Weights are staged once per CTA by cp.async.bulk and
 // read K-major (recompute) and MN-major (= W^T, data gradient) from the same image.
+#include <stdlib.h>
+
 #include "chain.cuh"
 
 namespace bsms {
@@ -41,6 +43,7 @@ struct EdgeBwdParams {
   int B, N, E;
   long long rows;
   int ntiles;
+  unsigned long long* prof;  // optional [16] per-phase cycle counters (BSMS_PHASE_PROF=1), summed over CTAs
 };
 
 __device__ __forceinline__ uint32_t tile_off(int r, int chunk) {  // 16-byte chunk `chunk` (0..15) of row r
@@ -136,6 +139,20 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
   uint8_t* s_gy = sp;  // the W2 slot: W2 is idle between the first recompute GEMM and the last data-gradient GEMM,
                        // so gy lives there meanwhile and W2 is brought back by cp.async.bulk (32 KB from L2 per tile)
   uint32_t wacc = 0;  // weight-gradient accumulators hold something
+  // optional phase profile: thread 0 accumulates the cycles between consecutive marks
+  unsigned long long* s_prof = reinterpret_cast<unsigned long long*>(s_tmem + 2);  // [16]
+  long long tprev = 0;
+  if (p.prof && tid == 0) {
+    for (int k = 0; k < 16; ++k) s_prof[k] = 0ull;
+    tprev = clock64();
+  }
+  auto mark = [&](int k) {
+    if (p.prof && tid == 0) {
+      const long long t = clock64();
+      s_prof[k] += (unsigned long long)(t - tprev);
+      tprev = t;
+    }
+  };
   // persistent per-thread partial sums for the bias / fiber-weight gradients (channel cc, row half rh)
   float4 acc_b[4];  // bias-gradient partial sums of this lane's 4 channels; [0] unused (acc_b0 below)
 #pragma unroll
@@ -223,6 +240,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       s_ij[tid] = ij;
     }
     __syncthreads();
+    mark(0);
     const long long row = (long long)tile * 128 + r;
     const bool valid = row < p.rows;
     const int rowj = s_ij[r].y;
@@ -294,20 +312,25 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     // ---- recompute the forward chain
     gather_a0();
     sync_all();
+    mark(1);
     if (tid == 0) {
       issue_gemm(aT[0], aW[0], false);
       mma_commit(bar_m);
     }
     wait_mma();
+    mark(2);
     act_epilogue(s_bias + 128, s_T[1], m1);
     sync_all();
+    mark(3);
     if (tid == 0) {
       issue_gemm(aT[1], aW[1], false);
       mma_commit(bar_m);
     }
     wait_mma();
+    mark(4);
     act_epilogue(s_bias + 256, s_T[2], m2);
     sync_all();
+    mark(5);
     if (tid == 0) {
       issue_gemm(aT[2], aW[2], false);
       mma_commit(bar_m);
@@ -323,6 +346,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       }
     }
     wait_mma();
+    mark(6);
     // ---- LayerNorm backward: gy = rstd * (g - mean(g) - yhat * mean(g * yhat)) -> T0
     //      two sweeps over this thread's 64 accumulator columns, 32 at a time (register budget)
     {
@@ -372,6 +396,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       }
     }
     sync_all();
+    mark(7);
     if (tid == 0) {
       issue_wgrad(tmem_base + 384, aW[0], aT[2]);  // dW4 += gy^T a2
       issue_gemm(aW[0], aW[2], true);              // D = gy W4
@@ -384,8 +409,10 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       mbar_expect_tx(bar_r, kWBlk);
       bulk_g2s(aW[0], p.wpack, kWBlk, bar_r);
     }
+    mark(8);
     grad_epilogue(m2, s_T[2]);  // g2 -> T2
     sync_all();
+    mark(9);
     if (tid == 0) {
       issue_wgrad(tmem_base + 256, aT[2], aT[1]);  // dW3 += g2^T a1
       issue_gemm(aT[2], aW[1], true);              // D = g2 W3
@@ -393,8 +420,10 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     }
     colsum(s_T[2], acc_b[2]);
     wait_mma();
+    mark(10);
     grad_epilogue(m1, s_T[1]);  // g1 -> T1
     sync_all();
+    mark(11);
     if (tid == 0) {
       mbar_wait(bar_r, phase_r);                   // W2 is back
       issue_wgrad(tmem_base + 128, aT[1], aT[0]);  // dW2 += g1^T a0
@@ -405,6 +434,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     phase_r ^= 1;
     colsum(s_T[1], acc_b[1]);
     wait_mma();
+    mark(12);
     // ---- g0 = D . [a0 > 0] (mask re-derived from the a0 tile) -> fp32 staging over T1|T2, 16-byte
     //      chunks XOR-swizzled by row so that both the row-thread writes and the row-cooperative reads
     //      below are bank-conflict free
@@ -432,6 +462,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       }
     }
     __syncthreads();
+    mark(13);
     {
       // row-cooperative pass (warp w: rows 16w..16w+15, lane l: channels 4l..4l+3): the gradient of the
       // sender projection goes out as one coalesced 512 B red.add per edge row; the gradient of the
@@ -460,8 +491,12 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       if (cur >= 0) red_add_v4(p.gPsPd + (size_t)cur * 256 + 128 + 4 * lane, run.x, run.y, run.z, run.w);
     }
     __syncthreads();  // the staging tiles / row metadata are rewritten by the next tile
+    mark(14);
   }
 
+  if (p.prof && tid == 0) {
+    for (int k = 0; k < 16; ++k) atomicAdd(p.prof + k, s_prof[k]);
+  }
   // ---- flush: weight-gradient accumulators (TMEM) and the per-thread bias / fiber partial sums
   fence_before_sync();
   __syncthreads();
@@ -502,7 +537,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
 }
 
 // alignment slack + 3 weight slots + 3 tiles + s_bias[512] + s_F[128] + s_fib[128] + s_x[2][128] + s_ij[128] + 3 barriers + TMEM address
-size_t edge_chain_bwd_smem() { return 1024 + 6 * kWBlk + 512 * 4 + 128 * 16 * 2 + 256 * 16 + 128 * 8 + 3 * 8 + 16; }
+size_t edge_chain_bwd_smem() { return 1024 + 6 * kWBlk + 512 * 4 + 128 * 16 * 2 + 256 * 16 + 128 * 8 + 3 * 8 + 16 + 128; }
 
 // Fused bf16 backward of the edge stage.  gPsPd must be zero-filled; gW/gb/gW1 are accumulated into.
 int edge_chain_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const bsms_gmp_grads* gr, const float* PsPd,
@@ -547,11 +582,27 @@ int edge_chain_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, co
     k_pack_weights<1><<<3, 256, 0, st>>>(pk, wpack);
     BSMS_LAUNCHED();
   }
+  static const bool phase_prof = getenv("BSMS_PHASE_PROF") != nullptr;
+  static unsigned long long* d_prof = nullptr;
+  p.prof = nullptr;
+  if (phase_prof) {
+    if (!d_prof) BSMS_CUDA(cudaMalloc(&d_prof, 16 * sizeof(unsigned long long)));
+    BSMS_CUDA(cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), st));
+    p.prof = d_prof;
+  }
   const size_t smem = edge_chain_bwd_smem();
   BSMS_CUDA(cudaFuncSetAttribute(k_edge_chain_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope ps_(PK_EDGE_CHAIN_BWD, st);
   k_edge_chain_bwd<<<std::min(sms, p.ntiles), 256, smem, st>>>(p);
   BSMS_LAUNCHED();
+  if (phase_prof) {  // debug aid: per-phase cycles per tile (thread 0 of every CTA), printed per launch
+    unsigned long long h[16];
+    BSMS_CUDA(cudaMemcpyAsync(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost, st));
+    BSMS_CUDA(cudaStreamSynchronize(st));
+    fprintf(stderr, "[bwd phases] tiles %d:", p.ntiles);
+    for (int k = 0; k < 15; ++k) fprintf(stderr, " %llu", h[k] / (unsigned long long)p.ntiles);
+    fprintf(stderr, "\n");
+  }
   return BSMS_OK;
 }
 
