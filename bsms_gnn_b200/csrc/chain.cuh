@@ -58,6 +58,55 @@ __device__ __forceinline__ void coop_gather_a0(const float* __restrict__ PsPd, c
   }
 }
 
+// The same gather, software-pipelined: the loads of the next U rows are issued before the current U rows
+// are combined, so a warp that gathers alone on its scheduler (warp-specialised producer) keeps 2U
+// row requests in flight instead of stalling on every batch.  (r_end - r_begin) must be a multiple of U.
+template <int U>
+__device__ __forceinline__ void coop_gather_a0_pipe(const float* __restrict__ PsPd, const int2* s_ij, const float4* s_fib,
+                                                    const float4 (&Fl)[4], uint8_t* tile, int r_begin, int r_end, int lane,
+                                                    float* dbg, long long dbg_row0) {
+  const uint32_t col_off = (uint32_t)((lane >> 4) * 16384 + (lane & 1) * 8);
+  const int chunk7 = (lane >> 1) & 7;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 a[2][U], d[2][U];
+  auto issue = [&](int r, float4 (&aa)[U], float4 (&dd)[U]) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int2 ij = s_ij[r + u];
+      const bool ok = ij.x >= 0;
+      aa[u] = ok ? ld4(PsPd + (size_t)ij.x * 256 + 4 * lane) : z4;
+      dd[u] = ok ? ld4(PsPd + (size_t)ij.y * 256 + 128 + 4 * lane) : z4;
+    }
+  };
+  auto combine = [&](int r, const float4 (&aa)[U], const float4 (&dd)[U]) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float4 f = s_fib[r + u];
+      float x0 = aa[u].x + dd[u].x, x1 = aa[u].y + dd[u].y, x2 = aa[u].z + dd[u].z, x3 = aa[u].w + dd[u].w;
+      x0 = x0 + Fl[0].x * f.x + Fl[0].y * f.y + Fl[0].z * f.z + Fl[0].w * f.w;
+      x1 = x1 + Fl[1].x * f.x + Fl[1].y * f.y + Fl[1].z * f.z + Fl[1].w * f.w;
+      x2 = x2 + Fl[2].x * f.x + Fl[2].y * f.y + Fl[2].z * f.z + Fl[2].w * f.w;
+      x3 = x3 + Fl[3].x * f.x + Fl[3].y * f.y + Fl[3].z * f.z + Fl[3].w * f.w;
+      x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+      if (dbg && s_ij[r + u].x >= 0) st4(dbg + (dbg_row0 + r + u) * 128 + 4 * lane, make_float4(x0, x1, x2, x3));
+      uint2 pk;
+      pk.x = pack_bf16(x0, x1);
+      pk.y = pack_bf16(x2, x3);
+      *reinterpret_cast<uint2*>(tile + col_off + (r + u) * 128 + ((chunk7 ^ ((r + u) & 7)) << 4)) = pk;
+    }
+  };
+  issue(r_begin, a[0], d[0]);
+#pragma unroll 1
+  for (int r = r_begin; r < r_end; r += 2 * U) {
+    if (r + U < r_end) issue(r + U, a[1], d[1]);
+    combine(r, a[0], d[0]);
+    if (r + U < r_end) {
+      if (r + 2 * U < r_end) issue(r + 2 * U, a[0], d[0]);
+      combine(r + U, a[1], d[1]);
+    }
+  }
+}
+
 // Row-cooperative load of NR contiguous-in-index rows (tile rows r_begin .. r_begin+NR-1 = global rows
 // row0 + r) into registers (lane l: channels 4l..4l+3 of each row; rows past `rows` read as zero), and
 // their conversion into a K-major SWIZZLE_128B bf16 operand tile.  Split so that the loads of the NEXT

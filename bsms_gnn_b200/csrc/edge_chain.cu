@@ -447,6 +447,305 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------
+// k_edge_chain_ws: the bf16 edge stage, warp-specialised.  384 threads:
+//   warps 0-7  : two CONSUMER warpgroups, each owning one 128-edge tile at a time (thread = edge row = TMEM
+//                lane): SS-form first MMA from the a0 tile, two TS-form layers, LayerNorm, row-cooperative
+//                segmented reduce — never touch the gather;
+//   warps 8-11 : one PRODUCER warpgroup that runs ahead over BOTH consumers' tile sequences: row metadata
+//                (indices, fiber), L2 prefetch of the tile after, software-pipelined row-cooperative gather of
+//                Ps[src] + Pd[dst] into a ring of three 32 KB a0 operand tiles.
+// Hand-off through mbarriers (full[buf]: 4 producer-warp arrivals; empty[buf]: 4 consumer-warp arrivals
+// after the segmented reduce, whose staging aliases the tile).  The three biases share ONE 16 KB B block
+// (K columns 0 / 16 / 32 of the 64-wide swizzle atom), which is what makes room for the third a0 tile.
+constexpr int kWsBuf = 3;
+
+// b2, b3, b4 -> one block in the K-major SW128 image: element (n, 16 l) = bias_l[n], rest 0
+__global__ void k_pack_bias3(const float* b2, const float* b3, const float* b4, uint8_t* __restrict__ out) {
+  for (int i = threadIdx.x; i < (int)kBiasBlk / 16; i += blockDim.x) reinterpret_cast<uint4*>(out)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 384; i += blockDim.x) {
+    const int l = i >> 7, n = i & 127;
+    const float* b = l == 0 ? b2 : (l == 1 ? b3 : b4);
+    *reinterpret_cast<__nv_bfloat16*>(out + wblk_offset(n, 16 * l)) = __float2bfloat16_rn(b[n]);
+  }
+}
+
+__global__ void __launch_bounds__(384, 1) k_edge_chain_ws(const EdgeChainParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t IDESC = make_idesc(1, 128, 128);
+  const uint32_t s0 = smem_u32(smem_raw);
+  const uint32_t sbase = (s0 + 1023u) & ~1023u;
+  uint8_t* sp = smem_raw + (sbase - s0);
+  const uint32_t bias_blk = sbase + 3 * kWBlk;     // 16 KB
+  const uint32_t a0_blk = bias_blk + kBiasBlk;     // ring of kWsBuf tiles
+  uint8_t* s_a0 = sp + 3 * kWBlk + kBiasBlk;
+  float4* s_F = reinterpret_cast<float4*>(s_a0 + kWsBuf * kWBlk);  // [128]
+  float4* s_fib = s_F + 128;                                       // [kWsBuf][128]
+  int2* s_ij = reinterpret_cast<int2*>(s_fib + kWsBuf * 128);      // [kWsBuf][128]
+  int* s_tgt = reinterpret_cast<int*>(s_ij + kWsBuf * 128);        // [kWsBuf][128]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tgt + kWsBuf * 128);  // w, m[2], full[3], empty[3]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 9);
+  unsigned long long* s_prof = reinterpret_cast<unsigned long long*>(s_tmem + 2);  // [16]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar_w = smem_u32(&s_bar[0]);
+  auto bar_full = [&](int b) { return smem_u32(&s_bar[3 + b]); };
+  auto bar_empty = [&](int b) { return smem_u32(&s_bar[6 + b]); };
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(smem_u32(&s_bar[1]), 1);
+    mbar_init(smem_u32(&s_bar[2]), 1);
+    for (int b = 0; b < kWsBuf; ++b) {
+      mbar_init(bar_full(b), 4);
+      mbar_init(bar_empty(b), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
+  if (tid < 128) {
+    const int ldw1 = 2 * kD + p.P + 1;
+    float f[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k <= p.P; ++k) f[k] = p.W1[(size_t)tid * ldw1 + k];
+    s_F[tid] = make_float4(f[0], f[1], f[2], f[3]);
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+  if (tid == 0) {
+    mbar_expect_tx(bar_w, 3 * kWBlk + kBiasBlk);
+    for (int blk = 0; blk < 3; ++blk) bulk_g2s(sbase + blk * kWBlk, p.wpack + (size_t)blk * kWBlk, kWBlk, bar_w);
+    bulk_g2s(bias_blk, p.bpack, kBiasBlk, bar_w);
+  }
+  // tile sequence of this CTA, shared by both roles: seq -> (tile, consumer seq & 1, buffer seq % 3)
+  const int tstride = gridDim.x * 2;
+  auto tile_of = [&](int seq) { return (int)blockIdx.x * 2 + (seq & 1) + (seq >> 1) * tstride; };
+
+  if (warp >= 8) {
+    // ================================================================= PRODUCER (128 threads)
+    const int tw = tid - 256, q = warp - 8;
+    float4 Fl[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) Fl[c] = s_F[4 * lane + c];
+    for (int seq = 0; tile_of(seq) < p.ntiles; ++seq) {
+      const int tile = tile_of(seq), buf = seq % kWsBuf;
+      if (seq >= kWsBuf) mbar_wait(bar_empty(buf), ((seq / kWsBuf) - 1) & 1);
+      const long long row = (long long)tile * 128 + tw;
+      float fib[4] = {0.f, 0.f, 0.f, 0.f};
+      int2 ij = make_int2(-1, -1);
+      if (row < p.rows) {
+        const int b = (int)(row / p.E);
+        const int e = (int)(row - (long long)b * p.E);
+        const int i = p.src_d[e], j = p.dst_d[e];
+        const float* pb = p.pos + (p.pos_batched ? (size_t)b * p.N * p.P : 0);
+        float nrm = 0.f;
+        for (int k = 0; k < p.P; ++k) {
+          float dlt = pb[(size_t)i * p.P + k] - pb[(size_t)j * p.P + k];
+          fib[k] = dlt;
+          nrm += dlt * dlt;
+        }
+        fib[p.P] = sqrtf(nrm);
+        ij = make_int2(b * p.N + i, b * p.N + j);
+      }
+      s_ij[buf * 128 + tw] = ij;
+      s_fib[buf * 128 + tw] = make_float4(fib[0], fib[1], fib[2], fib[3]);
+      s_tgt[buf * 128 + tw] = ij.y;
+      {
+        // pull the rows of the tile after this one into L2 while this one is gathered
+        const int ntile = tile_of(seq + 1);
+        const long long nrow = (long long)ntile * 128 + tw;
+        if (ntile < p.ntiles && nrow < p.rows) {
+          const int nb = (int)(nrow / p.E);
+          const int ne = (int)(nrow - (long long)nb * p.E);
+          const float* nps = p.PsPd + ((size_t)nb * p.N + p.src_d[ne]) * 256;
+          const float* npd = p.PsPd + ((size_t)nb * p.N + p.dst_d[ne]) * 256 + 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nps + k * 32));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(npd + k * 32));
+          }
+        }
+      }
+      __syncwarp();  // warp q gathers exactly the 32 rows its own lanes described
+      coop_gather_a0_pipe<4>(p.PsPd, s_ij + buf * 128, s_fib + buf * 128, Fl, s_a0 + buf * kWBlk, q * 32, q * 32 + 32, lane,
+                             p.dbg_stage == 0 ? p.dbg : nullptr, (long long)tile * 128);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full(buf));
+    }
+  } else {
+    // ================================================================= CONSUMERS (2 x 128 threads)
+    const int wg = warp >> 2, tw = tid & 127, q = warp & 3;
+    const uint32_t bar_m = smem_u32(&s_bar[1 + wg]);
+    const uint32_t d_tmem = tmem_base + wg * 256;
+    const uint32_t a_tmem = d_tmem + 128;
+    const uint32_t ones_tmem = d_tmem + 192;  // 16 columns, element k=0 is 1.0
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    {
+      uint32_t ones[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) ones[t] = 0u;
+      ones[0] = 0x00003F80u;  // bf16 pair (1.0, 0.0)
+      tmem_st16(ones_tmem + lane_off, ones);
+    }
+    uint32_t phase = 0;
+    bool weights_ready = false;
+    long long tprev = 0;
+    if (p.prof && tid == 0) {
+      for (int k = 0; k < 16; ++k) s_prof[k] = 0ull;
+      tprev = clock64();
+    }
+    auto mark = [&](int k) {
+      if (p.prof && tid == 0) {
+        const long long t = clock64();
+        s_prof[k] += (unsigned long long)(t - tprev);
+        tprev = t;
+      }
+    };
+    for (int seq = wg; tile_of(seq) < p.ntiles; seq += 2) {
+      const int tile = tile_of(seq), buf = seq % kWsBuf;
+      const long long row = (long long)tile * 128 + tw;
+      const bool valid = row < p.rows;
+      mark(0);
+      mbar_wait(bar_full(buf), (seq / kWsBuf) & 1);
+      mark(1);
+      const int* tgt = s_tgt + buf * 128 + q * 32;
+      const int my_tgt = tgt[lane];
+      // run starts of the dst-sorted rows of this warp (bit rr set: row rr starts a new destination)
+      const int prev_tgt = __shfl_up_sync(0xffffffffu, my_tgt, 1);
+      const uint32_t startmask = __ballot_sync(0xffffffffu, lane == 0 || my_tgt != prev_tgt);
+#pragma unroll 1
+      for (int layer = 0; layer < 3; ++layer) {
+        wait_st();
+        fence_before_sync();
+        bar_sync(1 + wg, 128);
+        mark(2 + 3 * layer);
+        if (tw == 0) {
+          if (!weights_ready) {
+            mbar_wait(bar_w, 0);
+            weights_ready = true;
+          }
+          fence_after_sync();
+          const uint32_t wb = sbase + layer * kWBlk;
+          // D = ones x [bias_l | 0]^T  (bias l sits at K columns 16 l of the shared bias block)
+          mma_ts(d_tmem, ones_tmem, smem_desc_sw128(bias_blk + layer * 32, 16, 1024), IDESC, 0);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t koff = (ks >> 2) * 16384 + (ks & 3) * 32;
+            const uint64_t bhi = smem_desc_sw128(wb + koff, 16, 1024);
+            if (layer == 0)
+              mma_ss(d_tmem, smem_desc_sw128(a0_blk + buf * kWBlk + koff, 16, 1024), bhi, IDESC, 1u);
+            else
+              mma_ts(d_tmem, a_tmem + ks * 8, bhi, IDESC, 1u);
+          }
+          mma_commit(bar_m);
+        }
+        mbar_wait(bar_m, phase);
+        phase ^= 1;
+        fence_after_sync();
+        mark(3 + 3 * layer);
+        if (layer < 2) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(d_tmem + lane_off + c0, r);
+            wait_ld();
+            float v[32];
+#pragma unroll
+            for (int t = 0; t < 32; ++t) v[t] = fmaxf(__uint_as_float(r[t]), 0.f);
+            if (p.dbg && p.dbg_stage == layer + 1 && valid) {
+#pragma unroll
+              for (int t = 0; t < 32; ++t) p.dbg[row * 128 + c0 + t] = v[t];
+            }
+            store_act32<1>(a_tmem + lane_off, c0, v);
+          }
+          mark(4 + 3 * layer);
+        } else {
+          // ---- final: LayerNorm over the row.  Pass 1: shifted sums (shift = first element, so the
+          //      one-pass variance has no cancellation); pass 2: normalise + segmented reduce by dst.
+          float shift = 0.f, sum = 0.f, ssq = 0.f;
+#pragma unroll 1
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(d_tmem + lane_off + c0, r);
+            wait_ld();
+            if (c0 == 0) shift = __uint_as_float(r[0]);
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+              const float dlt = __uint_as_float(r[t]) - shift;
+              sum += dlt;
+              ssq = fmaf(dlt, dlt, ssq);
+            }
+          }
+          const float mean_d = sum * (1.f / 128.f);
+          const float var = fmaxf(ssq * (1.f / 128.f) - mean_d * mean_d, 0.f);
+          const float rstd = 1.f / sqrtf(var + 1e-5f);
+          const float mean = shift + mean_d;
+          mark(10);
+          // Pass 2, row-cooperative: the warp's 32 normalised rows go through its private 8 KB of the
+          // (dead) a0 tile, 64 channels at a time ([32][64] fp32, 16-byte chunks XOR-swizzled by row);
+          // then each half-warp walks 16 of the dst-sorted rows with lane = 4 channels and flushes every
+          // finished run of equal destination with ONE 16-byte red.add per lane (256 B per half-warp).
+          float* wstage = reinterpret_cast<float*>(s_a0 + buf * kWBlk + q * 8192);
+          const int l16 = lane & 15, hw = lane >> 4;
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            __syncwarp();
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              uint32_t r[32];
+              tmem_ld32(d_tmem + lane_off + 64 * half + 32 * cc, r);
+              wait_ld();
+              if (p.dbg && p.dbg_stage == 3 && valid) {
+#pragma unroll
+                for (int t = 0; t < 32; ++t) p.dbg[row * 128 + 64 * half + 32 * cc + t] = __uint_as_float(r[t]);
+              }
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                const float4 o = make_float4((__uint_as_float(r[4 * q4 + 0]) - mean) * rstd, (__uint_as_float(r[4 * q4 + 1]) - mean) * rstd,
+                                             (__uint_as_float(r[4 * q4 + 2]) - mean) * rstd, (__uint_as_float(r[4 * q4 + 3]) - mean) * rstd);
+                *reinterpret_cast<float4*>(wstage + lane * 64 + (((8 * cc + q4) ^ (lane & 15)) << 2)) = o;
+              }
+            }
+            __syncwarp();
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            int cur = -1;
+            float* dstc = p.aggr + 64 * half + 4 * l16;
+#pragma unroll 4
+            for (int k = 0; k < 16; ++k) {
+              const int rr = 16 * hw + k;
+              const float4 m = *reinterpret_cast<const float4*>(wstage + rr * 64 + ((l16 ^ k) << 2));
+              if (k == 0 || ((startmask >> rr) & 1u)) {
+                if (cur >= 0) red_add_v4(dstc + (size_t)cur * 128, acc.x, acc.y, acc.z, acc.w);
+                cur = tgt[rr];
+                acc = m;
+              } else {
+                acc.x += m.x; acc.y += m.y; acc.z += m.z; acc.w += m.w;
+              }
+            }
+            if (cur >= 0) red_add_v4(dstc + (size_t)cur * 128, acc.x, acc.y, acc.z, acc.w);
+          }
+          // this warp is done with the tile buffer (staging and row metadata): hand it back to the producer
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_empty(buf));
+        }
+      }
+    }
+    mark(11);
+    if (p.prof && tid == 0)
+      for (int k = 0; k < 16; ++k) atomicAdd(p.prof + k, s_prof[k]);
+  }
+  // teardown
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+static size_t edge_chain_ws_smem() {
+  return 1024 + 3 * kWBlk + kBiasBlk + kWsBuf * kWBlk + 128 * 16 + kWsBuf * 128 * (16 + 8 + 4) + 9 * 8 + 16 + 128;
+}
+
 template <int NSPLIT, int CH>
 static size_t edge_chain_smem() {
   return 1024 + 3 * NSPLIT * kWBlk + (NSPLIT == 1 ? 3 * kBiasBlk + 2 * kWBlk : 0) + 384 * 4 + 128 * 16 + 256 * 16 + 256 * 8 +
@@ -518,14 +817,13 @@ int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, con
     }
     {
       ProfScope ps_(PK_OTHER, st);
-      k_pack_bias<<<3, 128, 0, st>>>(w->b_edge[1], w->b_edge[2], w->b_edge[3], bpack);
+      k_pack_bias3<<<1, 128, 0, st>>>(w->b_edge[1], w->b_edge[2], w->b_edge[3], bpack);
       BSMS_LAUNCHED();
     }
-    auto kern = k_edge_chain<1, 32>;
-    const size_t smem = edge_chain_smem<1, 32>();
-    BSMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = edge_chain_ws_smem();
+    BSMS_CUDA(cudaFuncSetAttribute(k_edge_chain_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps_(PK_EDGE_CHAIN, st);
-    kern<<<grid, 256, smem, st>>>(p);
+    k_edge_chain_ws<<<grid, 384, smem, st>>>(p);
     BSMS_LAUNCHED();
     if (report() != BSMS_OK) return BSMS_ECUDA;
   } else {
