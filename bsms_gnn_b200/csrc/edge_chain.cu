@@ -162,12 +162,12 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
   for (int c = 0; c < 4; ++c) Fl[c] = s_F[4 * lane + c];
 
   long long tprev = 0;
-  if (p.prof && tid == 0) {
+  if (false && tid == 0) {
     for (int k = 0; k < 16; ++k) s_prof[k] = 0ull;
     tprev = clock64();
   }
   auto mark = [&](int k) {
-    if (p.prof && tid == 0) {
+    if (false && tid == 0) {
       const long long t = clock64();
       s_prof[k] += (unsigned long long)(t - tprev);
       tprev = t;
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
     }
   }
   mark(11);
-  if (p.prof && tid == 0)
+  if (false && tid == 0)
     for (int k = 0; k < 16; ++k) atomicAdd(p.prof + k, s_prof[k]);
   // teardown
   fence_before_sync();
@@ -471,6 +471,7 @@ __global__ void k_pack_bias3(const float* b2, const float* b3, const float* b4, 
   }
 }
 
+template <bool PROF>
 __global__ void __launch_bounds__(384, 1) k_edge_chain_ws(const EdgeChainParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t IDESC = make_idesc(1, 128, 128);
@@ -592,12 +593,12 @@ __global__ void __launch_bounds__(384, 1) k_edge_chain_ws(const EdgeChainParams 
     uint32_t phase = 0;
     bool weights_ready = false;
     long long tprev = 0;
-    if (p.prof && tid == 0) {
+    if (PROF && tid == 0) {
       for (int k = 0; k < 16; ++k) s_prof[k] = 0ull;
       tprev = clock64();
     }
     auto mark = [&](int k) {
-      if (p.prof && tid == 0) {
+      if (PROF && tid == 0) {
         const long long t = clock64();
         s_prof[k] += (unsigned long long)(t - tprev);
         tprev = t;
@@ -733,7 +734,7 @@ __global__ void __launch_bounds__(384, 1) k_edge_chain_ws(const EdgeChainParams 
       }
     }
     mark(11);
-    if (p.prof && tid == 0)
+    if (PROF && tid == 0)
       for (int k = 0; k < 16; ++k) atomicAdd(p.prof + k, s_prof[k]);
   }
   // teardown
@@ -821,9 +822,10 @@ int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, con
       BSMS_LAUNCHED();
     }
     const size_t smem = edge_chain_ws_smem();
-    BSMS_CUDA(cudaFuncSetAttribute(k_edge_chain_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = phase_prof ? k_edge_chain_ws<true> : k_edge_chain_ws<false>;
+    BSMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps_(PK_EDGE_CHAIN, st);
-    k_edge_chain_ws<<<grid, 384, smem, st>>>(p);
+    kern<<<grid, 384, smem, st>>>(p);
     BSMS_LAUNCHED();
     if (report() != BSMS_OK) return BSMS_ECUDA;
   } else {

@@ -80,6 +80,7 @@ __device__ __forceinline__ void load_d64(uint32_t taddr, float (&v)[64]) {
   }
 }
 
+template <bool PROF>
 __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t IDESC_KK = make_idesc(1, 128, 128, 0, 0);  // A K-major, B K-major   (recompute)
@@ -142,12 +143,12 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
   // optional phase profile: thread 0 accumulates the cycles between consecutive marks
   unsigned long long* s_prof = reinterpret_cast<unsigned long long*>(s_tmem + 2);  // [16]
   long long tprev = 0;
-  if (p.prof && tid == 0) {
+  if (PROF && tid == 0) {
     for (int k = 0; k < 16; ++k) s_prof[k] = 0ull;
     tprev = clock64();
   }
   auto mark = [&](int k) {
-    if (p.prof && tid == 0) {
+    if (PROF && tid == 0) {
       const long long t = clock64();
       s_prof[k] += (unsigned long long)(t - tprev);
       tprev = t;
@@ -494,7 +495,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     mark(14);
   }
 
-  if (p.prof && tid == 0) {
+  if (PROF && tid == 0) {
     for (int k = 0; k < 16; ++k) atomicAdd(p.prof + k, s_prof[k]);
   }
   // ---- flush: weight-gradient accumulators (TMEM) and the per-thread bias / fiber partial sums
@@ -591,9 +592,10 @@ int edge_chain_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, co
     p.prof = d_prof;
   }
   const size_t smem = edge_chain_bwd_smem();
-  BSMS_CUDA(cudaFuncSetAttribute(k_edge_chain_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kern = phase_prof ? k_edge_chain_bwd<true> : k_edge_chain_bwd<false>;
+  BSMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope ps_(PK_EDGE_CHAIN_BWD, st);
-  k_edge_chain_bwd<<<std::min(sms, p.ntiles), 256, smem, st>>>(p);
+  kern<<<std::min(sms, p.ntiles), 256, smem, st>>>(p);
   BSMS_LAUNCHED();
   if (phase_prof) {  // debug aid: per-phase cycles per tile (thread 0 of every CTA), printed per launch
     unsigned long long h[16];
