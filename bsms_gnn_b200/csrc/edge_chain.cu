@@ -448,14 +448,14 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
 }
 
 // ------------------------------------------------------------------------------------------
-// k_edge_chain_ws: the bf16 edge stage, warp-specialised.  384 threads:
+// k_edge_chain_ws: the bf16 edge stage, warp-specialised.  512 threads:
 //   warps 0-7  : two CONSUMER warpgroups, each owning one 128-edge tile at a time (thread = edge row = TMEM
 //                lane): SS-form first MMA from the a0 tile, two TS-form layers, LayerNorm, row-cooperative
 //                segmented reduce — never touch the gather;
-//   warps 8-11 : one PRODUCER warpgroup that runs ahead over BOTH consumers' tile sequences: row metadata
+//   warps 8-15 : eight PRODUCER warps (16 tile rows each) that run ahead over BOTH consumers' tile sequences: row metadata
 //                (indices, fiber), L2 prefetch of the tile after, software-pipelined row-cooperative gather of
 //                Ps[src] + Pd[dst] into a ring of three 32 KB a0 operand tiles.
-// Hand-off through mbarriers (full[buf]: 4 producer-warp arrivals; empty[buf]: 4 consumer-warp arrivals
+// Hand-off through mbarriers (full[buf]: 8 producer-warp arrivals; empty[buf]: 4 consumer-warp arrivals
 // after the segmented reduce, whose staging aliases the tile).  The three biases share ONE 16 KB B block
 // (K columns 0 / 16 / 32 of the 64-wide swizzle atom), which is what makes room for the third a0 tile.
 constexpr int kWsBuf = 3;
@@ -472,7 +472,7 @@ __global__ void k_pack_bias3(const float* b2, const float* b3, const float* b4, 
 }
 
 template <bool PROF>
-__global__ void __launch_bounds__(384, 1) k_edge_chain_ws(const EdgeChainParams p) {
+__global__ void __launch_bounds__(512, 1) k_edge_chain_ws(const EdgeChainParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t IDESC = make_idesc(1, 128, 128);
   const uint32_t s0 = smem_u32(smem_raw);
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(384, 1) k_edge_chain_ws(const EdgeChainParams 
     mbar_init(smem_u32(&s_bar[1]), 1);
     mbar_init(smem_u32(&s_bar[2]), 1);
     for (int b = 0; b < kWsBuf; ++b) {
-      mbar_init(bar_full(b), 4);
+      mbar_init(bar_full(b), 8);
       mbar_init(bar_empty(b), 4);
     }
     fence_mbar_init();
@@ -524,38 +524,41 @@ __global__ void __launch_bounds__(384, 1) k_edge_chain_ws(const EdgeChainParams 
   auto tile_of = [&](int seq) { return (int)blockIdx.x * 2 + (seq & 1) + (seq >> 1) * tstride; };
 
   if (warp >= 8) {
-    // ================================================================= PRODUCER (128 threads)
-    const int tw = tid - 256, q = warp - 8;
+    // ================================================================= PRODUCERS (8 warps, 16 tile rows each)
+    const int pw = warp - 8;
     float4 Fl[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) Fl[c] = s_F[4 * lane + c];
     for (int seq = 0; tile_of(seq) < p.ntiles; ++seq) {
       const int tile = tile_of(seq), buf = seq % kWsBuf;
       if (seq >= kWsBuf) mbar_wait(bar_empty(buf), ((seq / kWsBuf) - 1) & 1);
-      const long long row = (long long)tile * 128 + tw;
-      float fib[4] = {0.f, 0.f, 0.f, 0.f};
-      int2 ij = make_int2(-1, -1);
-      if (row < p.rows) {
-        const int b = (int)(row / p.E);
-        const int e = (int)(row - (long long)b * p.E);
-        const int i = p.src_d[e], j = p.dst_d[e];
-        const float* pb = p.pos + (p.pos_batched ? (size_t)b * p.N * p.P : 0);
-        float nrm = 0.f;
-        for (int k = 0; k < p.P; ++k) {
-          float dlt = pb[(size_t)i * p.P + k] - pb[(size_t)j * p.P + k];
-          fib[k] = dlt;
-          nrm += dlt * dlt;
+      if (lane < 16) {
+        // lanes 0-15: metadata of this warp's 16 rows
+        const int tr = pw * 16 + lane;
+        const long long row = (long long)tile * 128 + tr;
+        float fib[4] = {0.f, 0.f, 0.f, 0.f};
+        int2 ij = make_int2(-1, -1);
+        if (row < p.rows) {
+          const int b = (int)(row / p.E);
+          const int e = (int)(row - (long long)b * p.E);
+          const int i = p.src_d[e], j = p.dst_d[e];
+          const float* pb = p.pos + (p.pos_batched ? (size_t)b * p.N * p.P : 0);
+          float nrm = 0.f;
+          for (int k = 0; k < p.P; ++k) {
+            float dlt = pb[(size_t)i * p.P + k] - pb[(size_t)j * p.P + k];
+            fib[k] = dlt;
+            nrm += dlt * dlt;
+          }
+          fib[p.P] = sqrtf(nrm);
+          ij = make_int2(b * p.N + i, b * p.N + j);
         }
-        fib[p.P] = sqrtf(nrm);
-        ij = make_int2(b * p.N + i, b * p.N + j);
-      }
-      s_ij[buf * 128 + tw] = ij;
-      s_fib[buf * 128 + tw] = make_float4(fib[0], fib[1], fib[2], fib[3]);
-      s_tgt[buf * 128 + tw] = ij.y;
-      {
-        // pull the rows of the tile after this one into L2 while this one is gathered
+        s_ij[buf * 128 + tr] = ij;
+        s_fib[buf * 128 + tr] = make_float4(fib[0], fib[1], fib[2], fib[3]);
+        s_tgt[buf * 128 + tr] = ij.y;
+      } else {
+        // lanes 16-31: pull the rows of the tile after this one into L2 while this one is gathered
         const int ntile = tile_of(seq + 1);
-        const long long nrow = (long long)ntile * 128 + tw;
+        const long long nrow = (long long)ntile * 128 + pw * 16 + (lane - 16);
         if (ntile < p.ntiles && nrow < p.rows) {
           const int nb = (int)(nrow / p.E);
           const int ne = (int)(nrow - (long long)nb * p.E);
@@ -568,8 +571,8 @@ __global__ void __launch_bounds__(384, 1) k_edge_chain_ws(const EdgeChainParams 
           }
         }
       }
-      __syncwarp();  // warp q gathers exactly the 32 rows its own lanes described
-      coop_gather_a0_pipe<4>(p.PsPd, s_ij + buf * 128, s_fib + buf * 128, Fl, s_a0 + buf * kWBlk, q * 32, q * 32 + 32, lane,
+      __syncwarp();  // the warp gathers exactly the 16 rows its own lanes described
+      coop_gather_a0_pipe<4>(p.PsPd, s_ij + buf * 128, s_fib + buf * 128, Fl, s_a0 + buf * kWBlk, pw * 16, pw * 16 + 16, lane,
                              p.dbg_stage == 0 ? p.dbg : nullptr, (long long)tile * 128);
       fence_proxy_async();
       __syncwarp();
@@ -713,16 +716,25 @@ __global__ void __launch_bounds__(384, 1) k_edge_chain_ws(const EdgeChainParams 
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             int cur = -1;
             float* dstc = p.aggr + 64 * half + 4 * l16;
-#pragma unroll 4
-            for (int k = 0; k < 16; ++k) {
-              const int rr = 16 * hw + k;
-              const float4 m = *reinterpret_cast<const float4*>(wstage + rr * 64 + ((l16 ^ k) << 2));
-              if (k == 0 || ((startmask >> rr) & 1u)) {
-                if (cur >= 0) red_add_v4(dstc + (size_t)cur * 128, acc.x, acc.y, acc.z, acc.w);
-                cur = tgt[rr];
-                acc = m;
-              } else {
-                acc.x += m.x; acc.y += m.y; acc.z += m.z; acc.w += m.w;
+#pragma unroll
+            for (int k0 = 0; k0 < 16; k0 += 4) {
+              float4 m[4];
+              int tg[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {  // shared loads and target broadcasts of 4 rows ahead of their use
+                m[u] = *reinterpret_cast<const float4*>(wstage + (16 * hw + k0 + u) * 64 + ((l16 ^ (k0 + u)) << 2));
+                tg[u] = __shfl_sync(0xffffffffu, my_tgt, 16 * hw + k0 + u);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int rr = 16 * hw + k0 + u;
+                const bool start = (k0 + u == 0) || ((startmask >> rr) & 1u);
+                if (start && cur >= 0) red_add_v4(dstc + (size_t)cur * 128, acc.x, acc.y, acc.z, acc.w);
+                acc.x = start ? m[u].x : acc.x + m[u].x;
+                acc.y = start ? m[u].y : acc.y + m[u].y;
+                acc.z = start ? m[u].z : acc.z + m[u].z;
+                acc.w = start ? m[u].w : acc.w + m[u].w;
+                cur = start ? tg[u] : cur;
               }
             }
             if (cur >= 0) red_add_v4(dstc + (size_t)cur * 128, acc.x, acc.y, acc.z, acc.w);
@@ -825,7 +837,7 @@ int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, con
     auto kern = phase_prof ? k_edge_chain_ws<true> : k_edge_chain_ws<false>;
     BSMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps_(PK_EDGE_CHAIN, st);
-    kern<<<grid, 384, smem, st>>>(p);
+    kern<<<grid, 512, smem, st>>>(p);
     BSMS_LAUNCHED();
     if (report() != BSMS_OK) return BSMS_ECUDA;
   } else {
