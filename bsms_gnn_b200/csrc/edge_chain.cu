@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(512, 1) k_edge_chain_ws(const EdgeChainParams 
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 9);
   unsigned long long* s_prof = reinterpret_cast<unsigned long long*>(s_tmem + 2);  // [16]
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = (int)uniform(threadIdx.x >> 5), lane = tid & 31;
   const uint32_t bar_w = smem_u32(&s_bar[0]);
   auto bar_full = [&](int b) { return smem_u32(&s_bar[3 + b]); };
   auto bar_empty = [&](int b) { return smem_u32(&s_bar[6 + b]); };
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(512, 1) k_edge_chain_ws(const EdgeChainParams 
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_base = uniform(*s_tmem);
   if (tid == 0) {
     mbar_expect_tx(bar_w, 3 * kWBlk + kBiasBlk);
     for (int blk = 0; blk < 3; ++blk) bulk_g2s(sbase + blk * kWBlk, p.wpack + (size_t)blk * kWBlk, kWBlk, bar_w);
@@ -619,31 +619,34 @@ __global__ void __launch_bounds__(512, 1) k_edge_chain_ws(const EdgeChainParams 
       // run starts of the dst-sorted rows of this warp (bit rr set: row rr starts a new destination)
       const int prev_tgt = __shfl_up_sync(0xffffffffu, my_tgt, 1);
       const uint32_t startmask = __ballot_sync(0xffffffffu, lane == 0 || my_tgt != prev_tgt);
-#pragma unroll 1
+#pragma unroll
       for (int layer = 0; layer < 3; ++layer) {
         wait_st();
         fence_before_sync();
         bar_sync(1 + wg, 128);
         mark(2 + 3 * layer);
-        if (tw == 0) {
+        if (q == 0) {  // the first warp of the warpgroup issues: one elected lane, operands warp-uniform
           if (!weights_ready) {
             mbar_wait(bar_w, 0);
             weights_ready = true;
           }
           fence_after_sync();
-          const uint32_t wb = sbase + layer * kWBlk;
-          // D = ones x [bias_l | 0]^T  (bias l sits at K columns 16 l of the shared bias block)
-          mma_ts(d_tmem, ones_tmem, smem_desc_sw128(bias_blk + layer * 32, 16, 1024), IDESC, 0);
+          if (elect_one()) {
+            const uint32_t wb = sbase + layer * kWBlk;
+            // D = ones x [bias_l | 0]^T  (bias l sits at K columns 16 l of the shared bias block)
+            mma_ts(d_tmem, ones_tmem, smem_desc_sw128(bias_blk + layer * 32, 16, 1024), IDESC, 0);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint32_t koff = (ks >> 2) * 16384 + (ks & 3) * 32;
-            const uint64_t bhi = smem_desc_sw128(wb + koff, 16, 1024);
-            if (layer == 0)
-              mma_ss(d_tmem, smem_desc_sw128(a0_blk + buf * kWBlk + koff, 16, 1024), bhi, IDESC, 1u);
-            else
-              mma_ts(d_tmem, a_tmem + ks * 8, bhi, IDESC, 1u);
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint32_t koff = (ks >> 2) * 16384 + (ks & 3) * 32;
+              const uint64_t bhi = smem_desc_sw128(wb + koff, 16, 1024);
+              if (layer == 0)
+                mma_ss(d_tmem, smem_desc_sw128(a0_blk + buf * kWBlk + koff, 16, 1024), bhi, IDESC, 1u);
+              else
+                mma_ts(d_tmem, a_tmem + ks * 8, bhi, IDESC, 1u);
+            }
+            mma_commit(bar_m);
           }
-          mma_commit(bar_m);
+          __syncwarp();
         }
         mbar_wait(bar_m, phase);
         phase ^= 1;
@@ -814,7 +817,7 @@ int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, con
     BSMS_CUDA(cudaStreamSynchronize(st));
     const unsigned long long nt = (unsigned long long)((p.ntiles + 1) / 2);  // tiles seen by warpgroup 0
     fprintf(stderr, "[fwd phases] tiles %d:", p.ntiles);
-    for (int k = 0; k < 12; ++k) fprintf(stderr, " %llu", h[k] / nt);
+    for (int k = 0; k < 16; ++k) fprintf(stderr, " %llu", h[k] / nt);
     fprintf(stderr, "\n");
     return BSMS_OK;
   };

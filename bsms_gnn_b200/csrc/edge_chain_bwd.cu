@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
   const uint32_t aW[3] = {sbase, sbase + kWBlk, sbase + 2 * kWBlk};
   const uint32_t aT[3] = {sbase + 3 * kWBlk, sbase + 4 * kWBlk, sbase + 5 * kWBlk};
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = (int)uniform(threadIdx.x >> 5), lane = tid & 31;
   const int q = warp & 3, h = warp >> 2, r = q * 32 + lane;
   const uint32_t bar_w = smem_u32(&s_bar[0]), bar_m = smem_u32(&s_bar[1]), bar_r = smem_u32(&s_bar[2]);
 
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_base = uniform(*s_tmem);
   if (tid == 0) {
     mbar_expect_tx(bar_w, 3 * kWBlk);
     for (int blk = 0; blk < 3; ++blk) bulk_g2s(aW[blk], p.wpack + (size_t)blk * kWBlk, kWBlk, bar_w);
@@ -314,27 +314,36 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     gather_a0();
     sync_all();
     mark(1);
-    if (tid == 0) {
-      issue_gemm(aT[0], aW[0], false);
-      mma_commit(bar_m);
+    if (warp == 0) {  // one elected lane issues; operands are warp-uniform (no per-lane R2UR loop per MMA)
+      if (elect_one()) {
+        issue_gemm(aT[0], aW[0], false);
+        mma_commit(bar_m);
+      }
+      __syncwarp();
     }
     wait_mma();
     mark(2);
     act_epilogue(s_bias + 128, s_T[1], m1);
     sync_all();
     mark(3);
-    if (tid == 0) {
-      issue_gemm(aT[1], aW[1], false);
-      mma_commit(bar_m);
+    if (warp == 0) {
+      if (elect_one()) {
+        issue_gemm(aT[1], aW[1], false);
+        mma_commit(bar_m);
+      }
+      __syncwarp();
     }
     wait_mma();
     mark(4);
     act_epilogue(s_bias + 256, s_T[2], m2);
     sync_all();
     mark(5);
-    if (tid == 0) {
-      issue_gemm(aT[2], aW[2], false);
-      mma_commit(bar_m);
+    if (warp == 0) {
+      if (elect_one()) {
+        issue_gemm(aT[2], aW[2], false);
+        mma_commit(bar_m);
+      }
+      __syncwarp();
     }
     // upstream gradient row g_aggr[dst] (this thread's 64 channels): issued before the MMA wait
     float g[64];
@@ -398,10 +407,13 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     }
     sync_all();
     mark(7);
-    if (tid == 0) {
-      issue_wgrad(tmem_base + 384, aW[0], aT[2]);  // dW4 += gy^T a2
-      issue_gemm(aW[0], aW[2], true);              // D = gy W4
-      mma_commit(bar_m);
+    if (warp == 0) {
+      if (elect_one()) {
+        issue_wgrad(tmem_base + 384, aW[0], aT[2]);  // dW4 += gy^T a2
+        issue_gemm(aW[0], aW[2], true);              // D = gy W4
+        mma_commit(bar_m);
+      }
+      __syncwarp();
     }
     colsum(s_gy, acc_b[3]);
     __syncthreads();  // every warp is done reading gy through the generic proxy
@@ -414,10 +426,13 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     grad_epilogue(m2, s_T[2]);  // g2 -> T2
     sync_all();
     mark(9);
-    if (tid == 0) {
-      issue_wgrad(tmem_base + 256, aT[2], aT[1]);  // dW3 += g2^T a1
-      issue_gemm(aT[2], aW[1], true);              // D = g2 W3
-      mma_commit(bar_m);
+    if (warp == 0) {
+      if (elect_one()) {
+        issue_wgrad(tmem_base + 256, aT[2], aT[1]);  // dW3 += g2^T a1
+        issue_gemm(aT[2], aW[1], true);              // D = g2 W3
+        mma_commit(bar_m);
+      }
+      __syncwarp();
     }
     colsum(s_T[2], acc_b[2]);
     wait_mma();
@@ -425,13 +440,16 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     grad_epilogue(m1, s_T[1]);  // g1 -> T1
     sync_all();
     mark(11);
-    if (tid == 0) {
-      mbar_wait(bar_r, phase_r);                   // W2 is back
-      issue_wgrad(tmem_base + 128, aT[1], aT[0]);  // dW2 += g1^T a0
-      issue_gemm(aT[1], aW[0], true);              // D = g1 W2
-      mma_commit(bar_m);
-      wacc = 1;
+    if (warp == 0) {
+      mbar_wait(bar_r, phase_r);  // W2 is back
+      if (elect_one()) {
+        issue_wgrad(tmem_base + 128, aT[1], aT[0]);  // dW2 += g1^T a0
+        issue_gemm(aT[1], aW[0], true);              // D = g1 W2
+        mma_commit(bar_m);
+      }
+      __syncwarp();
     }
+    wacc = 1;
     phase_r ^= 1;
     colsum(s_T[1], acc_b[1]);
     wait_mma();

@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256, 2) k_lin2(const Lin2Params p) {
   float* s_bias = reinterpret_cast<float*>(sp + 2 * kWBlk + nblk * kWBlk);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 256);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = (int)uniform(threadIdx.x >> 5), lane = tid & 31;
   const uint32_t bar_w = smem_u32(&s_bar[0]), bar_m = smem_u32(&s_bar[1]);
   if (tid == 0) {
     mbar_init(bar_w, 1);
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(256, 2) k_lin2(const Lin2Params p) {
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_base = uniform(*s_tmem);
   if (tid == 0) {
     mbar_expect_tx(bar_w, nblk * kWBlk);
     for (int nb = 0; nb < p.NB; ++nb)
@@ -249,24 +249,27 @@ __global__ void __launch_bounds__(256, 2) k_lin2(const Lin2Params p) {
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {  // one elected lane issues; operands are warp-uniform (no per-lane R2UR loop per MMA)
       if (!weights_ready) {
         mbar_wait(bar_w, 0);
         weights_ready = true;
       }
       fence_after_sync();
-      for (int nb = 0; nb < p.NB; ++nb)
-        for (int kb = 0; kb < p.KB; ++kb) {
-          const uint32_t wb = w_addr + (nb * p.KB + kb) * kWBlk;
+      if (elect_one()) {
+        for (int nb = 0; nb < p.NB; ++nb)
+          for (int kb = 0; kb < p.KB; ++kb) {
+            const uint32_t wb = w_addr + (nb * p.KB + kb) * kWBlk;
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t ad = smem_desc_sw128(a_addr + kb * kWBlk + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
-            const uint32_t off = p.b_mn ? ks * 2048 : (ks >> 2) * 16384 + (ks & 3) * 32;
-            const uint64_t bd = smem_desc_sw128(wb + off, p.b_mn ? 16384 : 16, 1024);
-            mma_ss(tmem_base + nb * 128, ad, bd, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint64_t ad = smem_desc_sw128(a_addr + kb * kWBlk + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
+              const uint32_t off = p.b_mn ? ks * 2048 : (ks >> 2) * 16384 + (ks & 3) * 32;
+              const uint64_t bd = smem_desc_sw128(wb + off, p.b_mn ? 16384 : 16, 1024);
+              mma_ss(tmem_base + nb * 128, ad, bd, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+            }
           }
-        }
-      mma_commit(bar_m);
+        mma_commit(bar_m);
+      }
+      __syncwarp();
     }
     {
       const int next = tile + gridDim.x;
@@ -360,7 +363,7 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradBatch batch) {
   // stage s: G tile at (2s) * 32 KB, X tile at (2s+1) * 32 KB
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(sp + 4 * kWBlk);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = (int)uniform(threadIdx.x >> 5), lane = tid & 31;
   const uint32_t bar0 = smem_u32(&s_bar[0]), bar1 = smem_u32(&s_bar[1]);
   if (tid == 0) {
     mbar_init(bar0, 1);
@@ -371,7 +374,7 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradBatch batch) {
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_base = uniform(*s_tmem);
   const int cc = tid & 127, rh = tid >> 7;
   float acc_b = 0.f;
   uint32_t ph[2] = {0u, 0u};
@@ -400,16 +403,19 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradBatch batch) {
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       fence_after_sync();
-      const uint32_t ag = sbase + (2 * s) * kWBlk, ax = sbase + (2 * s + 1) * kWBlk;
+      if (elect_one()) {
+        const uint32_t ag = sbase + (2 * s) * kWBlk, ax = sbase + (2 * s + 1) * kWBlk;
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        const uint64_t ad = smem_desc_sw128(ag + ks * 2048, 16384, 1024);
-        const uint64_t bd = smem_desc_sw128(ax + ks * 2048, 16384, 1024);
-        mma_ss(tmem_base, ad, bd, IDESC_MM, (it > 0 || ks > 0) ? 1u : 0u);
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t ad = smem_desc_sw128(ag + ks * 2048, 16384, 1024);
+          const uint64_t bd = smem_desc_sw128(ax + ks * 2048, 16384, 1024);
+          mma_ss(tmem_base, ad, bd, IDESC_MM, (it > 0 || ks > 0) ? 1u : 0u);
+        }
+        mma_commit(s ? bar1 : bar0);
       }
-      mma_commit(s ? bar1 : bar0);
+      __syncwarp();
     }
     if (p.db) {  // bias gradient: column sums of the (bf16-rounded) G tile, overlapping the MMAs
       float sacc = 0.f;

@@ -38,6 +38,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
+// one lane of the (fully active) warp is elected; the compiler keeps the operands of the tcgen05 instructions
+// issued under it in uniform registers instead of emitting a per-lane R2UR loop around every MMA
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// warp-uniform broadcast (the compiler treats the result as uniform)
+__device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // ---------------------------------------------------------------- TMA 1-D bulk copy global -> smem
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
