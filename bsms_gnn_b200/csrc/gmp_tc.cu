@@ -22,6 +22,9 @@ int lin_tc2(const float* X0, int ldx0, const float* X1, int ldx1, int KB, int NB
             int ldadd1, float* Y0, int ldy0, float* Y1, int ldy1, float* ln_out, const float* res0, const float* res1,
             long long rows, int kind, cudaStream_t st);
 int wgrad_tc_batch(const WgradParams* probs, int nprob, cudaStream_t st);
+int node_chain_backward(const float* Yn, const float* g_out, const float* N1, const float* N2, const float* N3,
+                        const uint8_t* wpack_v2, float* G4, float* const* gW, float* const* gb, long long rows,
+                        cudaStream_t st);
 WgradParams wgrad_problem(const float* G, int ldg, const float* X, int ldx, float* dW, int ldo, float* db, long long rows);
 int launch_ln_residual(const float* Yn, const float* x, const float* skip, float* out, long long rows, cudaStream_t st);
 int launch_ln_bwd_rows(const float* Y, const float* g, int ldg, float* gY, long long rows, cudaStream_t st);
@@ -172,9 +175,7 @@ int gmp_backward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const 
   Arena ar(ws, ws_bytes);
   Arena sv(const_cast<float*>(saved), (size_t)-1);
   NodeBufs n = carve_nodes(saved ? sv : ar, Rn);
-  float* G1 = ar.take<float>(Rn * kD);
-  float* G2 = ar.take<float>(Rn * kD);
-  float* G3 = ar.take<float>(Rn * kD);
+  ar.take<float>(Rn * kD * 3);  // (three gradient buffers of the unfused path; kept so the workspace formula is unchanged)
   float* G4 = ar.take<float>(Rn * kD);
   float* gcat = ar.take<float>(Rn * 256);  // only the first Rn*128 floats are used (g_aggr)
   float* gPsPd = ar.take<float>(Rn * 256);
@@ -187,27 +188,16 @@ int gmp_backward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const 
   auto blk = [&](int i) { return (const uint8_t*)(wpack + (size_t)i * bs); };
   TC_TRY(pack_all(w, P, mode, wpack, st));
   if (!saved) TC_TRY(forward_nodes(pl, w, x, pos, pos_batched, B, P, mode, n, wpack, nullptr, nullptr, st));
-  // ---- node MLP backward: the data-gradient chain first, then ALL weight gradients in one launch
-  TC_TRY(launch_ln_bwd_rows(n.Yn, g_out, kD, G1, Rn, st));  // G1 = gYn
+  // ---- node MLP backward, layers 3..1: LayerNorm backward, data- and weight-gradient GEMMs in one fused kernel
   {
-    const float* gin[3] = {G1, G2, G3};
-    float* gout[3] = {G2, G3, G4};
-    const float* msk[3] = {n.N3, n.N2, n.N1};
-    const int bi[3] = {BV4, BV3, BV2};
-    for (int l = 0; l < 3; ++l) {
-      const uint8_t* b[1] = {blk(bi[l])};
-      TC_TRY(lin_tc2(gin[l], kD, nullptr, 0, 1, 1, b, 1, nullptr, 0, msk[l], kD, nullptr, 0, nullptr, 0, gout[l], kD, nullptr, 0,
-                     nullptr, nullptr, nullptr, Rn, PK_DGRAD, st));
-    }
+    float* gWn[3] = {gr->w_node[1], gr->w_node[2], gr->w_node[3]};
+    float* gbn[3] = {gr->b_node[1], gr->b_node[2], gr->b_node[3]};
+    TC_TRY(node_chain_backward(n.Yn, g_out, n.N1, n.N2, n.N3, blk(BV2), G4, gWn, gbn, Rn, st));
   }
   {
-    WgradParams pr[5] = {
-        wgrad_problem(G1, kD, n.N3, kD, gr->w_node[3], kD, gr->b_node[3], Rn),
-        wgrad_problem(G2, kD, n.N2, kD, gr->w_node[2], kD, gr->b_node[2], Rn),
-        wgrad_problem(G3, kD, n.N1, kD, gr->w_node[1], kD, gr->b_node[1], Rn),
-        wgrad_problem(G4, kD, x, kD, gr->w_node[0], 2 * kD, gr->b_node[0], Rn),         // layer 0: input [x | aggr]
-        wgrad_problem(G4, kD, n.aggr, kD, gr->w_node[0] + kD, 2 * kD, nullptr, Rn)};
-    TC_TRY(wgrad_tc_batch(pr, 5, st));
+    WgradParams pr[2] = {wgrad_problem(G4, kD, x, kD, gr->w_node[0], 2 * kD, gr->b_node[0], Rn),  // layer 0: input [x | aggr]
+                         wgrad_problem(G4, kD, n.aggr, kD, gr->w_node[0] + kD, 2 * kD, nullptr, Rn)};
+    TC_TRY(wgrad_tc_batch(pr, 2, st));
   }
   {
     // [g_x | g_aggr] = G4 V1: the x half leaves as g_x = g_out + ., the aggr half feeds the edge backward

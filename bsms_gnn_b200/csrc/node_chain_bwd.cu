@@ -1,0 +1,297 @@
+// Fused backward of the node MLP's layers 1..3 on tcgen05 (bf16 operands, fp32 accumulate): the
+// LayerNorm backward of the block output, three data-gradient GEMMs with their ReLU masks and three
+// weight-gradient GEMMs in ONE persistent kernel.  Nothing between the upstream gradient and the
+// gradient of the first layer's activation touches HBM (reference: src/ops/basic.py:6-23,97-98; the
+// reference's autograd materialises every intermediate).
+//
+// Per 128-node-row tile (256 threads; row-cooperative global I/O: one warp per 512 B row):
+//   G1 = LN'(Yn) g_out                     rows of Yn, g_out  -> TG (bf16 tile)      ; N3 rows -> T3
+//   dV4 += G1^T N3 ; G2 = (G1 V4) . [N3>0]  UMMA wgrad(TG,T3), dgrad D = TG x V4(MN)  -> T3 (in place) ; N2 rows -> T2
+//   dV3 += G2^T N2 ; G3 = (G2 V3) . [N2>0]  UMMA wgrad(T3,T2), dgrad D = T3 x V3(MN)  -> T2 (in place) ; N1 rows -> TG
+//   dV2 += G3^T N1 ; G4 = (G3 V2) . [N1>0]  UMMA wgrad(T2,TG), dgrad D = T2 x V2(MN)  -> fp32 staging over T3|T2 -> G4 rows
+// The loads of the next operand tile are issued in the shadow of the current MMA batch.  The three
+// weight-gradient accumulators stay in TMEM for the whole persistent loop (as in edge_chain_bwd.cu);
+// bias gradients are column sums of the staged gradient tiles.
+#include "chain.cuh"
+
+namespace bsms {
+
+struct NodeBwdParams {
+  const float* Yn;     // [rows,128] pre-LayerNorm output of the node MLP (kept from forward)
+  const float* g_out;  // [rows,128] gradient of the block output
+  const float* N[3];   // N1, N2, N3 [rows,128] (kept from forward)
+  const uint8_t* wpack;  // packed bf16 blocks V2, V3, V4 (contiguous)
+  float* G4;           // [rows,128] gradient of the first layer's activation (after its ReLU mask)
+  float* gW[3];        // V2, V3, V4 gradients [128,128] (accumulated)
+  float* gb[3];        // c2, c3, c4 gradients (accumulated)
+  long long rows;
+  int ntiles;
+};
+
+__device__ __forceinline__ uint32_t nt_off(int r, int chunk) {  // 16-byte chunk `chunk` (0..15) of tile row r
+  return (uint32_t)((chunk >> 3) * 16384 + r * 128 + (((chunk & 7) ^ (r & 7)) << 4));
+}
+
+__global__ void __launch_bounds__(256, 1) k_node_chain_bwd(const NodeBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t IDESC_KM = make_idesc(1, 128, 128, 0, 1);  // A K-major, B MN-major  (dgrad: B = W^T)
+  constexpr uint32_t IDESC_MM = make_idesc(1, 128, 128, 1, 1);  // A, B MN-major          (wgrad)
+  const uint32_t s0 = smem_u32(smem_raw);
+  const uint32_t sbase = (s0 + 1023u) & ~1023u;
+  uint8_t* sp = smem_raw + (sbase - s0);
+  // slots: [V2][V3][V4][TG][T3][T2]
+  uint8_t* s_TG = sp + 3 * kWBlk;
+  uint8_t* s_T3 = sp + 4 * kWBlk;
+  uint8_t* s_T2 = sp + 5 * kWBlk;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(sp + 6 * kWBlk);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
+  const uint32_t aV[3] = {sbase, sbase + kWBlk, sbase + 2 * kWBlk};
+  const uint32_t aTG = sbase + 3 * kWBlk, aT3 = sbase + 4 * kWBlk, aT2 = sbase + 5 * kWBlk;
+  float* s_stage = reinterpret_cast<float*>(s_T3);  // fp32 [128][128] over T3|T2
+
+  const int tid = threadIdx.x, warp = (int)uniform(threadIdx.x >> 5), lane = tid & 31;
+  const int q = warp & 3, h = warp >> 2, r = q * 32 + lane;
+  const uint32_t bar_w = smem_u32(&s_bar[0]), bar_m = smem_u32(&s_bar[1]);
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_m, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = uniform(*s_tmem);
+  if (tid == 0) {
+    mbar_expect_tx(bar_w, 3 * kWBlk);
+    for (int blk = 0; blk < 3; ++blk) bulk_g2s(aV[blk], p.wpack + (size_t)blk * kWBlk, kWBlk, bar_w);
+    mbar_wait(bar_w, 0);
+  }
+  const uint32_t d_tmem = tmem_base;  // D: cols [0,128); dV2/dV3/dV4: cols [128,256), [256,384), [384,512)
+  const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+  const uint32_t d_mine = d_tmem + lane_off + 64 * h;
+  uint32_t phase = 0, wacc = 0;
+  float4 acc_b[3];  // bias-gradient partial sums of this lane's 4 channels (c2, c3, c4)
+#pragma unroll
+  for (int l = 0; l < 3; ++l) acc_b[l] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  auto sync_all = [&]() {
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+  };
+  auto wait_mma = [&]() {
+    mbar_wait(bar_m, phase);
+    phase ^= 1;
+    fence_after_sync();
+  };
+  // dW[out][in] += G^T A (both MN-major views, K = 128 tile rows) followed by D = G(K-major) x W(MN-major = W^T)
+  auto issue_pair = [&](uint32_t dw_tmem, uint32_t g_tile, uint32_t a_tile, uint32_t w_blk) {
+    if (warp == 0) {
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t ad = smem_desc_sw128(g_tile + ks * 2048, 16384, 1024);
+          const uint64_t bd = smem_desc_sw128(a_tile + ks * 2048, 16384, 1024);
+          mma_ss(dw_tmem, ad, bd, IDESC_MM, (wacc | ks) != 0);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t ad = smem_desc_sw128(g_tile + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
+          const uint64_t bd = smem_desc_sw128(w_blk + ks * 2048, 16384, 1024);
+          mma_ss(d_tmem, ad, bd, IDESC_KM, ks > 0);
+        }
+        mma_commit(bar_m);
+      }
+      __syncwarp();
+    }
+  };
+  auto colsum = [&](const uint8_t* tile, float4& acc) {
+    const uint8_t* base = tile + (lane >> 4) * 16384 + (lane & 1) * 8;
+    const int chunk7 = (lane >> 1) & 7;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int rr = warp * 16; rr < warp * 16 + 16; ++rr) {
+      const uint2 u = *reinterpret_cast<const uint2*>(base + rr * 128 + ((chunk7 ^ (rr & 7)) << 4));
+      s.x += __uint_as_float(u.x << 16); s.y += __uint_as_float(u.x & 0xFFFF0000u);
+      s.z += __uint_as_float(u.y << 16); s.w += __uint_as_float(u.y & 0xFFFF0000u);
+    }
+    acc.x += s.x; acc.y += s.y; acc.z += s.z; acc.w += s.w;
+  };
+  // rows 16w..16w+15 of X -> bf16 tile (two batches of 8 rows in flight)
+  auto load_tile = [&](const float* X, long long row0, uint8_t* tile) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float4 v[8];
+      coop_rows_load<8>(X, kD, row0, p.rows, warp * 16 + 8 * half, lane, v);
+      coop_rows_store<8>(tile, warp * 16 + 8 * half, lane, v);
+    }
+  };
+  // gradient epilogue: D . [act > 0] -> the activation tile itself (in place, bf16)
+  auto grad_epilogue = [&](uint8_t* tile) {
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      uint32_t rr_[32];
+      tmem_ld32(d_mine + 32 * hh, rr_);
+      wait_ld();
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        uint4* cp = reinterpret_cast<uint4*>(tile + nt_off(r, 8 * h + 4 * hh + jj));
+        const uint4 a8 = *cp;
+        const uint32_t aw[4] = {a8.x, a8.y, a8.z, a8.w};
+        float o8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const uint32_t hw = (aw[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
+          o8[e] = hw ? __uint_as_float(rr_[8 * jj + e]) : 0.f;
+        }
+        uint4 u;
+        u.x = pack_bf16(o8[0], o8[1]); u.y = pack_bf16(o8[2], o8[3]);
+        u.z = pack_bf16(o8[4], o8[5]); u.w = pack_bf16(o8[6], o8[7]);
+        *cp = u;
+      }
+    }
+  };
+
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    const long long row0 = (long long)tile * 128;
+    // ---- G1 = LayerNorm backward of g_out through Yn (warp per row), N3 -> T3
+    {
+      const uint32_t col_off = (uint32_t)((lane >> 4) * 16384 + (lane & 1) * 8);
+      const int chunk7 = (lane >> 1) & 7;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float4 y[8], g[8];
+        coop_rows_load<8>(p.Yn, kD, row0, p.rows, warp * 16 + 8 * half, lane, y);
+        coop_rows_load<8>(p.g_out, kD, row0, p.rows, warp * 16 + 8 * half, lane, g);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int rr = warp * 16 + 8 * half + u;
+          const float mean = warp_sum(y[u].x + y[u].y + y[u].z + y[u].w) * (1.f / 128.f);
+          const float dx = y[u].x - mean, dy = y[u].y - mean, dz = y[u].z - mean, dw = y[u].w - mean;
+          const float var = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.f / 128.f);
+          const float rstd = 1.f / sqrtf(var + 1e-5f);
+          const float hx = dx * rstd, hy = dy * rstd, hz = dz * rstd, hw_ = dw * rstd;
+          const float c1 = warp_sum(g[u].x + g[u].y + g[u].z + g[u].w) * (1.f / 128.f);
+          const float c2 = warp_sum(g[u].x * hx + g[u].y * hy + g[u].z * hz + g[u].w * hw_) * (1.f / 128.f);
+          uint2 pk;  // rows past the end load zeros: y = g = 0 gives G1 = 0
+          pk.x = pack_bf16(rstd * (g[u].x - c1 - hx * c2), rstd * (g[u].y - c1 - hy * c2));
+          pk.y = pack_bf16(rstd * (g[u].z - c1 - hz * c2), rstd * (g[u].w - c1 - hw_ * c2));
+          *reinterpret_cast<uint2*>(s_TG + col_off + rr * 128 + ((chunk7 ^ (rr & 7)) << 4)) = pk;
+        }
+      }
+    }
+    load_tile(p.N[2], row0, s_T3);
+    sync_all();
+    issue_pair(tmem_base + 384, aTG, aT3, aV[2]);  // dV4 += G1^T N3 ; D = G1 V4
+    colsum(s_TG, acc_b[2]);
+    load_tile(p.N[1], row0, s_T2);                 // N2 -> T2 in the shadow of the MMAs
+    wait_mma();
+    grad_epilogue(s_T3);                           // G2 -> T3
+    sync_all();
+    issue_pair(tmem_base + 256, aT3, aT2, aV[1]);  // dV3 += G2^T N2 ; D = G2 V3
+    colsum(s_T3, acc_b[1]);
+    load_tile(p.N[0], row0, s_TG);                 // N1 -> TG (G1 is dead: its MMAs completed)
+    wait_mma();
+    grad_epilogue(s_T2);                           // G3 -> T2
+    sync_all();
+    issue_pair(tmem_base + 128, aT2, aTG, aV[0]);  // dV2 += G3^T N1 ; D = G3 V2
+    wacc = 1;
+    colsum(s_T2, acc_b[0]);
+    wait_mma();
+    __syncthreads();  // every warp is done with the column sums over T2 before the staging overwrites it
+    // ---- G4 = D . [N1 > 0] -> fp32 staging over T3|T2 (16-byte chunks XOR-swizzled by row)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      uint32_t rr_[32];
+      tmem_ld32(d_mine + 32 * hh, rr_);
+      wait_ld();
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const uint4 a8 = *reinterpret_cast<const uint4*>(s_TG + nt_off(r, 8 * h + 4 * hh + jj));
+        const uint32_t aw[4] = {a8.x, a8.y, a8.z, a8.w};
+        float o8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const uint32_t hw = (aw[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
+          o8[e] = hw ? __uint_as_float(rr_[8 * jj + e]) : 0.f;
+        }
+        const int c4 = 16 * h + 8 * hh + 2 * jj;
+        *reinterpret_cast<float4*>(s_stage + r * 128 + (((c4 + 0) ^ (r & 31)) << 2)) = make_float4(o8[0], o8[1], o8[2], o8[3]);
+        *reinterpret_cast<float4*>(s_stage + r * 128 + (((c4 + 1) ^ (r & 31)) << 2)) = make_float4(o8[4], o8[5], o8[6], o8[7]);
+      }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int rr = warp * 16; rr < warp * 16 + 16; ++rr) {
+      const long long row = row0 + rr;
+      if (row < p.rows)
+        st4(p.G4 + row * kD + 4 * lane, *reinterpret_cast<const float4*>(s_stage + rr * 128 + ((lane ^ (rr & 31)) << 2)));
+    }
+    __syncthreads();  // the tiles are rewritten by the next tile
+  }
+
+  // ---- flush: weight-gradient accumulators (TMEM) and the per-lane bias partial sums
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  if (wacc) {
+#pragma unroll 1
+    for (int l = 0; l < 3; ++l) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t rr_[32];
+        tmem_ld32(tmem_base + 128 * (l + 1) + lane_off + 64 * h + 32 * hh, rr_);
+        wait_ld();
+        float* dst = p.gW[l] + (size_t)r * 128 + 64 * h + 32 * hh;  // TMEM lane = output channel
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4)
+          red_add_v4(dst + q4 * 4, __uint_as_float(rr_[q4 * 4]), __uint_as_float(rr_[q4 * 4 + 1]),
+                     __uint_as_float(rr_[q4 * 4 + 2]), __uint_as_float(rr_[q4 * 4 + 3]));
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+      atomicAdd(p.gb[l] + 4 * lane + 0, acc_b[l].x);
+      atomicAdd(p.gb[l] + 4 * lane + 1, acc_b[l].y);
+      atomicAdd(p.gb[l] + 4 * lane + 2, acc_b[l].z);
+      atomicAdd(p.gb[l] + 4 * lane + 3, acc_b[l].w);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// G4 = gradient of the first node layer's activation; accumulates dV2..dV4 and dc2..dc4.
+int node_chain_backward(const float* Yn, const float* g_out, const float* N1, const float* N2, const float* N3,
+                        const uint8_t* wpack_v2, float* G4, float* const* gW, float* const* gb, long long rows,
+                        cudaStream_t st) {
+  if (rows == 0) return BSMS_OK;
+  NodeBwdParams p;
+  p.Yn = Yn;
+  p.g_out = g_out;
+  p.N[0] = N1;
+  p.N[1] = N2;
+  p.N[2] = N3;
+  p.wpack = wpack_v2;
+  p.G4 = G4;
+  for (int l = 0; l < 3; ++l) {
+    p.gW[l] = gW[l];
+    p.gb[l] = gb[l];
+  }
+  p.rows = rows;
+  p.ntiles = ceil_div(rows, 128);
+  int dev = 0, sms = 148;
+  BSMS_CUDA(cudaGetDevice(&dev));
+  BSMS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const size_t smem = 1024 + 6 * kWBlk + 2 * 8 + 16;
+  BSMS_CUDA(cudaFuncSetAttribute(k_node_chain_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope ps_(PK_DGRAD, st);
+  k_node_chain_bwd<<<std::min(sms, p.ntiles), 256, smem, st>>>(p);
+  BSMS_LAUNCHED();
+  return BSMS_OK;
+}
+
+}  // namespace bsms
