@@ -209,21 +209,31 @@ def run_mesh(args):
         step(h_dev)
     barrier()
     n0l = _lib.launch_count()
+    step(h_dev)
+    launches_per_step = _lib.launch_count() - n0l
+    run = lambda: step(h_dev)
+    if not args.no_graph:
+        # the whole step (forward, backward, halo exchanges, gradient all-reduce) replayed from ONE CUDA graph
+        from bsms_gnn_b200.graphed import GraphedStep
+        run = GraphedStep(lambda: step(h_dev), warmup=1)
+        for _ in range(2):
+            run()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as cs:
         e0.record()
         for _ in range(args.steps):
-            step(h_dev)
+            run()
         e1.record()
         barrier()
-    launches = _lib.launch_count() - n0l
+    launches = launches_per_step * args.steps
     ms = e0.elapsed_time(e1) / args.steps
-    h_in = torch.empty_like(h_dev).requires_grad_(True)
+    # end to end: this step's features come from pinned host memory, the loss goes back to the host
     t1 = time.perf_counter()
     for _ in range(args.steps):
         with torch.no_grad():
-            h_in.copy_(h_host, non_blocking=True)
-        _ = step(h_in).item()
+            h_dev.copy_(h_host, non_blocking=True)
+        _ = run().item()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t1) / args.steps
     if world > 1:
@@ -242,14 +252,24 @@ def run_mesh(args):
                                    f"latent 128, B=1, fwd+bwd", "mode": args.mode,
                        "parallelism": (f"node partition x{world}, {4 * depth + 1} halo exchanges per forward (NCCL p2p), "
                                        f"grad all-reduce") if world > 1 else "single GPU",
+                       "execution": "eager" if args.no_graph else "whole step replayed from one CUDA graph",
                        "rank0_ghost_rows_per_level": ghosts, "setup_s": setup_s,
                        "l2": "per-step working set far exceeds the 126 MB L2"},
             "edge_evals_per_s": edge_rows / (ms * 1e-3),
             "clocks": {"sm_mhz": clk.get("sm_mhz"), "sm_max_mhz": clk.get("sm_max_mhz"), "reasons": clk.get("reasons")},
             "e2e": {"value": E0 / e2e_s / 1e6, "unit": "M-edges/s", "h2d_bytes_per_step": int(h_host.numel() * 4),
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3},
-            "gpu_launches": int(launches)}))
+            "gpu_launches": int(launches)}), flush=True)
     if world > 1:
+        if not args.no_graph:
+            # a process group whose NCCL work was captured into a live CUDA graph does not tear down cleanly:
+            # drop the graph, drain the device and leave without the collective destructor
+            del run
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
@@ -322,6 +342,7 @@ def main():
     ap.add_argument("--nx", type=int, default=72)
     ap.add_argument("--depth", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="mesh workload: run the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--workload", default="airfoil", choices=["airfoil", "mesh", "rollout"],
                     help="airfoil: BASELINE.json's metric config (batch-parallel over GPUs); mesh: one large "
                          "node-partitioned mesh, B=1 (config 5: --nx 1414 = 2.0 M nodes / 12.0 M edges)")

@@ -235,6 +235,7 @@ class PartitionedBSGMP(torch.nn.Module):
         self.states = [RankState(p, device) for p in plans]
         self.ex = exchanger
         self.depth = model.unet_depth
+        self._pos_key, self._pos_cache = None, None
 
     @staticmethod
     def _gmp(gmp, x_loc, lv, p_loc):
@@ -254,22 +255,39 @@ class PartitionedBSGMP(torch.nn.Module):
             return hc_loc.new_zeros(0, hc_loc.shape[-1])
         return _PProlong.apply(hc_loc.contiguous(), lv)[:lv.n_own]
 
+    def _positions(self, pos_own):
+        """Local positions [owned | ghosts] of every level.  They depend on the positions only (the transfer
+        weights are topology-only), so for a static mesh they are exchanged and restricted ONCE and reused
+        while the caller passes the same, unmodified position tensors (identity + version check)."""
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in pos_own)
+        if key == self._pos_key:
+            return self._pos_cache
+        d, S, ex = self.depth, self.states, self.ex
+        R = range(len(S))
+        with torch.no_grad():
+            p = [t.detach().to(torch.float32).contiguous() for t in pos_own]
+            pos_loc = []
+            for l in range(d):
+                p_loc = ex.exchange(S, l, p)
+                pos_loc.append(p_loc)
+                p = [self._restrict(p_loc[r], S[r].levels[l]) for r in R]
+            pos_loc.append(ex.exchange(S, d, p))
+        self._pos_key, self._pos_cache = key, pos_loc
+        return pos_loc
+
     def forward(self, h_own, pos_own):
         d, S, ex, m = self.depth, self.states, self.ex, self.model
         R = range(len(S))
         x = [t.contiguous() for t in h_own]
-        p = [t.detach().to(torch.float32).contiguous() for t in pos_own]
-        skips, pos_loc = [], []
+        pos_loc = self._positions(pos_own)
+        skips = []
         for l in range(d):
-            x_loc, p_loc = ex.exchange(S, l, x), ex.exchange(S, l, p)
-            pos_loc.append(p_loc)
+            x_loc, p_loc = ex.exchange(S, l, x), pos_loc[l]
             y = [self._gmp(m.down_gmps[l], x_loc[r], S[r].levels[l], p_loc[r]) for r in R]
             skips.append(y)
             y_loc = ex.exchange(S, l, y)
             x = [self._restrict(y_loc[r], S[r].levels[l]) for r in R]
-            with torch.no_grad():
-                p = [self._restrict(p_loc[r], S[r].levels[l]) for r in R]
-        x_loc, p_loc = ex.exchange(S, d, x), ex.exchange(S, d, p)
+        x_loc, p_loc = ex.exchange(S, d, x), pos_loc[d]
         x = [self._gmp(m.bottom_gmp, x_loc[r], S[r].levels[d], p_loc[r]) for r in R]
         for k in range(d):
             l = d - 1 - k
