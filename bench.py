@@ -496,17 +496,21 @@ def main():
         fwd_passes = 1 if tensor_mode else 2  # fp32 FFMA edge layers also run in backward's recompute
         # algorithmic work of each kernel class in ONE fwd+bwd step (DESIGN.md "Kernels"):
         #   FLOPs for the dense kernels, gather-counted bytes for the bandwidth kernels
-        flops = {"edge_fwd_gemm": fwd_passes * Re * 3 * 2 * D * D, "dgrad": (Re * 3 + Rn * 7) * 2 * D * D,
-                 "wgrad": (Re * 3 + Rn * 8) * 2 * D * D, "node_fwd_gemm": 2 * Rn * 7 * 2 * D * D,
+        #   (bf16 mode: "dgrad" = fused node chain (3 dgrad + 3 wgrad GEMMs) + 4 layer-0 dgrad blocks per node row,
+        #    "wgrad" = the 4 layer-0 weight-gradient blocks per node row; the edge GEMMs live in edge_chain*)
+        flops = {"edge_fwd_gemm": fwd_passes * Re * 3 * 2 * D * D,
+                 "dgrad": (Rn * 10 if args.mode == "bf16" else Re * 3 + Rn * 7) * 2 * D * D,
+                 "wgrad": (Rn * 4 if args.mode == "bf16" else Re * 3 + Rn * 8) * 2 * D * D,
+                 "node_fwd_gemm": 2 * Rn * 7 * 2 * D * D,
                  "edge_chain": Re * 3 * 2 * D * D,
                  "edge_chain_bwd": Re * 9 * 2 * D * D}  # 3 recompute + 3 data-gradient + 3 weight-gradient GEMMs
         byts = {"edge_combine": 2 * (Re * (2 * D * 4 + 16 + 8 + D * 4)), "ln_segsum": 2 * (Re * D * 4 + Rn * D * 4),
                 "ln_bwd": Re * 3 * D * 4 + Rn * 3 * D * 4, "edge_grad_segsum": 2 * Re * D * 4 + Rn * 2 * D * 4,
                 "edge_chain": Re * (2 * D * 4 + 2 * 2 * 4 + 2 * 4) + Rn * D * 4,
-                # backward: the two projected rows are gathered twice (a0 is re-formed for its weight gradient),
-                # one upstream-gradient row is gathered, one gradient row is scattered per edge (sender side),
-                # the receiver side is reduced per destination run first
-                "edge_chain_bwd": Re * (4 * D * 4 + D * 4 + 2 * 2 * 4 + 2 * 4 + D * 4) + Rn * D * 4}
+                # backward: the two projected rows are gathered ONCE (a0 stays in shared memory for its weight
+                # gradient), one upstream-gradient row is gathered, one gradient row is scattered per edge (sender
+                # side); the receiver side is reduced per destination run first (one row per node)
+                "edge_chain_bwd": Re * (2 * D * 4 + D * 4 + D * 4 + 2 * 2 * 4 + 2 * 4) + Rn * D * 4}
         breakdown = {k: {"ms_per_step": v[0] / prof_steps, "launches_per_step": v[1] / prof_steps}
                      for k, v in prof.items() if v[1]}
         total_ms = sum(v["ms_per_step"] for v in breakdown.values())
@@ -516,11 +520,18 @@ def main():
             r = {"kernel": kind, "share_of_step": tms / total_ms, "traffic": None,
                  "avg_launch_us": 1e3 * tms / breakdown[kind]["launches_per_step"]}
             if kind in ("edge_chain", "edge_chain_bwd") and args.mode == "bf16":
-                # 1x bf16 MMA: HBM (gather-counted) is the governing bound, SURVEY.md §8d
+                # 1x bf16 MMA: the governing bound is the slower of the gather-counted HBM floor
+                # and the tensor-pipe floor; for both fused kernels that is HBM
                 ach = byts[kind] / (tms * 1e-3) / 1e9
+                tfl = flops[kind] / (tms * 1e-3) / 1e12
+                hbm_floor_ms = byts[kind] / (pk["hbm_gbs"] * 1e9) * 1e3
+                tensor_floor_ms = flops[kind] / (pk["bf16_tflops_sustained"] * 1e12) * 1e3
                 r.update(bound="hbm", achieved=ach, peak=pk["hbm_gbs"], unit="GB/s", frac=ach / pk["hbm_gbs"],
-                         peak_source=pk["source"],
-                         tensor_tflops=flops[kind] / (tms * 1e-3) / 1e12)
+                         peak_source=pk["source"], tensor_tflops=tfl, hbm_floor_ms=hbm_floor_ms,
+                         tensor_floor_ms=tensor_floor_ms, algorithmic_bytes_per_step=byts[kind])
+                if tensor_floor_ms > hbm_floor_ms:
+                    r.update(bound="tensor", achieved=tfl, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
+                             frac=tfl / pk["bf16_tflops_sustained"])
             elif kind in flops:
                 ach = flops[kind] / (tms * 1e-3) / 1e12
                 peak = pk["bf16_tflops_sustained"]
