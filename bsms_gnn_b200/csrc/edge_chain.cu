@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 3);
   unsigned long long* s_prof = reinterpret_cast<unsigned long long*>(s_tmem + 2);  // [16]
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = (int)uniform(threadIdx.x >> 5), lane = tid & 31;
   const int wg = warp >> 2, tw = tid & 127, q = warp & 3;
   const uint32_t bar_w = smem_u32(&s_bar[0]);
   const uint32_t bar_m = smem_u32(&s_bar[1 + wg]);
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_base = uniform(*s_tmem);
   if (tid == 0) {
     mbar_expect_tx(bar_w, NW * kWBlk + (BIAS_MMA ? 3 * kBiasBlk : 0));
     for (int blk = 0; blk < NW; ++blk) bulk_g2s(sbase + blk * kWBlk, p.wpack + (size_t)blk * kWBlk, kWBlk, bar_w);
@@ -274,30 +274,33 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
       fence_before_sync();
       bar_sync(1 + wg, 128);
       mark(2 + 3 * layer);
-      if (tw == 0) {
+      if (q == 0) {  // the first warp of the warpgroup issues: one elected lane, operands warp-uniform
         if (!weights_ready) {
           mbar_wait(bar_w, 0);
           weights_ready = true;
         }
         fence_after_sync();
-        const uint32_t wb = sbase + layer * NSPLIT * kWBlk;
-        if (BIAS_MMA)  // D = ones x [bias | 0]^T
-          mma_ts(d_tmem, ones_tmem, smem_desc_sw128(bias_blk + layer * kBiasBlk, 16, 1024), IDESC, 0);
+        if (elect_one()) {
+          const uint32_t wb = sbase + layer * NSPLIT * kWBlk;
+          if (BIAS_MMA)  // D = ones x [bias | 0]^T
+            mma_ts(d_tmem, ones_tmem, smem_desc_sw128(bias_blk + layer * kBiasBlk, 16, 1024), IDESC, 0);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t koff = (ks >> 2) * 16384 + (ks & 3) * 32;
-          const uint64_t bhi = smem_desc_sw128(wb + koff, 16, 1024);
-          if (COOP && layer == 0)
-            mma_ss(d_tmem, smem_desc_sw128(a0_blk + wg * kWBlk + koff, 16, 1024), bhi, IDESC, 1u);
-          else
-            mma_ts(d_tmem, a_tmem + ks * 8, bhi, IDESC, (BIAS_MMA || ks > 0) ? 1u : 0u);
-          if (NSPLIT == 2) {
-            const uint64_t blo = smem_desc_sw128(wb + kWBlk + koff, 16, 1024);
-            mma_ts(d_tmem, a_tmem + 64 + ks * 8, bhi, IDESC, 1);
-            mma_ts(d_tmem, a_tmem + ks * 8, blo, IDESC, 1);
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t koff = (ks >> 2) * 16384 + (ks & 3) * 32;
+            const uint64_t bhi = smem_desc_sw128(wb + koff, 16, 1024);
+            if (COOP && layer == 0)
+              mma_ss(d_tmem, smem_desc_sw128(a0_blk + wg * kWBlk + koff, 16, 1024), bhi, IDESC, 1u);
+            else
+              mma_ts(d_tmem, a_tmem + ks * 8, bhi, IDESC, (BIAS_MMA || ks > 0) ? 1u : 0u);
+            if (NSPLIT == 2) {
+              const uint64_t blo = smem_desc_sw128(wb + kWBlk + koff, 16, 1024);
+              mma_ts(d_tmem, a_tmem + 64 + ks * 8, bhi, IDESC, 1);
+              mma_ts(d_tmem, a_tmem + ks * 8, blo, IDESC, 1);
+            }
           }
+          mma_commit(bar_m);
         }
-        mma_commit(bar_m);
+        __syncwarp();
       }
       mbar_wait(bar_m, phase);
       phase ^= 1;

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(128, 2) k_lin(const LinParams p) {
   float* s_bias = reinterpret_cast<float*>(sp + 2 * BLK);  // [256]
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 256);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = (int)uniform(threadIdx.x >> 5);
   const uint32_t bar_w = smem_u32(&s_bar[0]), bar_m = smem_u32(&s_bar[1]);
   if (tid == 0) {
     mbar_init(bar_w, 1);
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(128, 2) k_lin(const LinParams p) {
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_base = uniform(*s_tmem);
   if (tid == 0) {
     mbar_expect_tx(bar_w, nblk * BLK);
     for (int nb = 0; nb < p.NB; ++nb)
@@ -106,22 +106,25 @@ __global__ void __launch_bounds__(128, 2) k_lin(const LinParams p) {
         }
         fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {  // one elected lane issues; operands are warp-uniform
           fence_after_sync();
-          const uint32_t wb = sbase + (nb * p.KB + kb) * BLK;
+          if (elect_one()) {
+            const uint32_t wb = sbase + (nb * p.KB + kb) * BLK;
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint32_t off = p.b_mn ? ks * 2048 : (ks >> 2) * 16384 + (ks & 3) * 32;
-            const uint32_t lbo = p.b_mn ? 16384 : 16;
-            const uint64_t bhi = smem_desc_sw128(wb + off, lbo, 1024);
-            mma_ts(d_tmem, a_tmem + ks * 8, bhi, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-            if (NSPLIT == 2) {
-              const uint64_t blo = smem_desc_sw128(wb + kWBlk + off, lbo, 1024);
-              mma_ts(d_tmem, a_tmem + 64 + ks * 8, bhi, idesc, 1);
-              mma_ts(d_tmem, a_tmem + ks * 8, blo, idesc, 1);
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint32_t off = p.b_mn ? ks * 2048 : (ks >> 2) * 16384 + (ks & 3) * 32;
+              const uint32_t lbo = p.b_mn ? 16384 : 16;
+              const uint64_t bhi = smem_desc_sw128(wb + off, lbo, 1024);
+              mma_ts(d_tmem, a_tmem + ks * 8, bhi, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+              if (NSPLIT == 2) {
+                const uint64_t blo = smem_desc_sw128(wb + kWBlk + off, lbo, 1024);
+                mma_ts(d_tmem, a_tmem + 64 + ks * 8, bhi, idesc, 1);
+                mma_ts(d_tmem, a_tmem + ks * 8, blo, idesc, 1);
+              }
             }
+            mma_commit(bar_m);
           }
-          mma_commit(bar_m);
+          __syncwarp();
         }
         mbar_wait(bar_m, phase);
         phase ^= 1;
@@ -255,20 +258,31 @@ __global__ void __launch_bounds__(256, 2) k_lin2(const Lin2Params p) {
         weights_ready = true;
       }
       fence_after_sync();
-      if (elect_one()) {
-        for (int nb = 0; nb < p.NB; ++nb)
-          for (int kb = 0; kb < p.KB; ++kb) {
-            const uint32_t wb = w_addr + (nb * p.KB + kb) * kWBlk;
+      // the loops run in warp-uniform control flow (whole warp), only the MMAs sit under the elected lane
+      for (int nb = 0; nb < p.NB; ++nb)
+        for (int kb = 0; kb < p.KB; ++kb) {
+          const uint32_t wb = w_addr + (nb * p.KB + kb) * kWBlk;
+          const uint32_t ab = a_addr + kb * kWBlk;
+          const uint32_t dt = tmem_base + nb * 128;
+          const uint32_t acc0 = kb > 0 ? 1u : 0u;
+          if (p.b_mn) {
+            if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-              const uint64_t ad = smem_desc_sw128(a_addr + kb * kWBlk + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
-              const uint32_t off = p.b_mn ? ks * 2048 : (ks >> 2) * 16384 + (ks & 3) * 32;
-              const uint64_t bd = smem_desc_sw128(wb + off, p.b_mn ? 16384 : 16, 1024);
-              mma_ss(tmem_base + nb * 128, ad, bd, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+              for (int ks = 0; ks < 8; ++ks)
+                mma_ss(dt, smem_desc_sw128(ab + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
+                       smem_desc_sw128(wb + ks * 2048, 16384, 1024), idesc, ks > 0 ? 1u : acc0);
+            }
+          } else {
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                mma_ss(dt, smem_desc_sw128(ab + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
+                       smem_desc_sw128(wb + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024), idesc, ks > 0 ? 1u : acc0);
             }
           }
-        mma_commit(bar_m);
-      }
+          __syncwarp();
+        }
+      if (elect_one()) mma_commit(bar_m);
       __syncwarp();
     }
     {
