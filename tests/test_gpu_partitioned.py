@@ -44,5 +44,18 @@ def test_partitioned_matches_global(hname, world, mode, ftol, gtol):
     (loss / h.numel()).backward()
     assert max_rel(out, ref.detach()) < ftol
     assert max_rel(hp.grad, ref_gh) < gtol
+    # second call with the same position tensors: the cached local positions (exchanged / restricted once for a
+    # static mesh) must give the same result; a modified position tensor must invalidate the cache
+    p_own = [pos.to(dev)[o] for o in own]
+    with torch.no_grad():
+        a = pm([h[o] for o in own], p_own)
+        key = pm._pos_key
+        b = pm([h[o] for o in own], p_own)
+        assert pm._pos_key == key
+        for x, y in zip(a, b):
+            assert max_rel(y, x) < (2e-6 if mode != "fp32" else 1e-7) or torch.equal(x, y)
+        p_own[0].mul_(1.0)  # bumps the version counter
+        pm([h[o] for o in own], p_own)
+        assert pm._pos_key != key
     for k, v in model.named_parameters():
         assert max_rel(v.grad, ref_grads[k]) < gtol, k
