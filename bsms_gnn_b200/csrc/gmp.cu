@@ -349,7 +349,8 @@ using namespace bsms;
 extern "C" size_t bsms_gmp_saved_bytes(int32_t B, int32_t N) {
   size_t Rn = (size_t)B * N;
   auto f = [](size_t n) { return align_up(n * sizeof(float), 256); };
-  return f(Rn * 256) + 5 * f(Rn * D) + 256;
+  // node-level tensors + the packed 16-bit weight images of this GMP (the bf16 backward reuses them: 1 MB)
+  return f(Rn * 256) + 5 * f(Rn * D) + 256 + (1u << 20);
 }
 
 extern "C" size_t bsms_gmp_workspace_bytes(int32_t B, int32_t N, int32_t E, int32_t mode, int32_t backward) {

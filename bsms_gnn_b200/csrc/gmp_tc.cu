@@ -156,7 +156,8 @@ int gmp_forward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const f
   Arena ar(ws, ws_bytes);
   Arena sv(saved, (size_t)-1);
   NodeBufs n = carve_nodes(saved ? sv : ar, Rn);
-  uint8_t* wpack = ar.take<uint8_t>(kScratchBytes);
+  // with `saved` the packed weight images are kept next to the node tensors so that backward does not re-pack
+  uint8_t* wpack = saved ? sv.take<uint8_t>(kScratchBytes) : ar.take<uint8_t>(kScratchBytes);
   if (!ar.ok()) {
     set_error("bsms_gmp_forward: workspace too small for the tensor-core path");
     return BSMS_EWORKSPACE;
@@ -175,6 +176,7 @@ int gmp_backward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const 
   Arena ar(ws, ws_bytes);
   Arena sv(const_cast<float*>(saved), (size_t)-1);
   NodeBufs n = carve_nodes(saved ? sv : ar, Rn);
+  uint8_t* saved_pack = saved ? sv.take<uint8_t>(kScratchBytes) : nullptr;  // packed by forward (same weights)
   ar.take<float>(Rn * kD * 3);  // (three gradient buffers of the unfused path; kept so the workspace formula is unchanged)
   float* G4 = ar.take<float>(Rn * kD);
   float* gcat = ar.take<float>(Rn * 256);  // only the first Rn*128 floats are used (g_aggr)
@@ -185,8 +187,11 @@ int gmp_backward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const 
     return BSMS_EWORKSPACE;
   }
   const size_t bs = gmp_pack_stride(mode);
+  if (saved_pack)
+    wpack = saved_pack;
+  else
+    TC_TRY(pack_all(w, P, mode, wpack, st));
   auto blk = [&](int i) { return (const uint8_t*)(wpack + (size_t)i * bs); };
-  TC_TRY(pack_all(w, P, mode, wpack, st));
   if (!saved) TC_TRY(forward_nodes(pl, w, x, pos, pos_batched, B, P, mode, n, wpack, nullptr, nullptr, st));
   // ---- node MLP backward, layers 3..1: LayerNorm backward, data- and weight-gradient GEMMs in one fused kernel
   {

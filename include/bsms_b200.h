@@ -143,7 +143,8 @@ size_t bsms_gmp_workspace_bytes(int32_t B, int32_t n_nodes, int32_t n_edges, int
                                 int32_t backward);
 /* `saved` (may be NULL): bsms_gmp_saved_bytes(B, n_nodes) bytes that receive the node-level
  * intermediates (projected rows, aggregated messages, node-MLP activations; no per-edge tensor)
- * so that backward does not recompute them. */
+ * and the packed 16-bit weight images of this call, so that backward neither recomputes nor
+ * re-packs them.  The weights must not change between the forward and its backward. */
 size_t bsms_gmp_saved_bytes(int32_t B, int32_t n_nodes);
 int bsms_gmp_forward(const bsms_level_plan* plan, const bsms_gmp_weights* w, const float* x,
                      const float* pos, int32_t pos_batched, const float* skip /* may be NULL */,
