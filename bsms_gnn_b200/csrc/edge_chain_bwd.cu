@@ -92,10 +92,10 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
   uint8_t* s_T[3] = {sp + 3 * kWBlk, sp + 4 * kWBlk, sp + 5 * kWBlk};
   float* s_bias = reinterpret_cast<float*>(sp + 6 * kWBlk);  // [4][128]
   float4* s_F = reinterpret_cast<float4*>(s_bias + 512);     // [128]
-  float4* s_fib = s_F + 128;                                 // [128] fiber of each tile row
-  float4* s_x = s_fib + 128;                                 // [2][128] LayerNorm partial sums
-  int2* s_ij = reinterpret_cast<int2*>(s_x + 256);           // [128] (b*N+src, b*N+dst) of each tile row, -1 past the end
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_ij + 128);
+  float4* s_fib2 = s_F + 128;                                // [2][128] fiber of each tile row (double-buffered)
+  float4* s_x = s_fib2 + 256;                                // [2][128] LayerNorm partial sums
+  int2* s_ij2 = reinterpret_cast<int2*>(s_x + 256);          // [2][128] (b*N+src, b*N+dst) of each tile row, -1 past the end
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_ij2 + 256);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 3);
   const uint32_t aW[3] = {sbase, sbase + kWBlk, sbase + 2 * kWBlk};
   const uint32_t aT[3] = {sbase + 3 * kWBlk, sbase + 4 * kWBlk, sbase + 5 * kWBlk};
@@ -210,16 +210,21 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     }
     acc.x += s.x; acc.y += s.y; acc.z += s.z; acc.w += s.w;
   };
-  auto gather_a0 = [&]() {
+  auto gather_a0 = [&](const int2* s_ij, const float4* s_fib) {
     float4 Fl[4];  // fiber coefficients of this lane's 4 channels
 #pragma unroll
     for (int c = 0; c < 4; ++c) Fl[c] = s_F[4 * lane + c];
     coop_gather_a0<8>(p.PsPd, s_ij, s_fib, Fl, s_T[0], warp * 16, warp * 16 + 16, lane, nullptr, 0);
   };
 
-  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-    // ---- row metadata (first 128 threads: one tile row each), then everything reads it from smem
-    if (tid < 128) {
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    // ---- row metadata, double-buffered (first 128 threads: one tile row each).  Only the first tile computes
+    //      it here; the metadata of every later tile is produced in three stages inside the recompute GEMM
+    //      waits of the tile before it (index loads / position loads / fiber), where every thread idles anyway.
+    float4* s_fib = s_fib2 + (it & 1) * 128;
+    int2* s_ij = s_ij2 + (it & 1) * 128;
+    if (it == 0 && tid < 128) {
       const long long row_ = (long long)tile * 128 + tid;
       float fib_[4] = {0.f, 0.f, 0.f, 0.f};
       int2 ij = make_int2(-1, -1);
@@ -292,26 +297,8 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       }
     };
 
-    // ---- pull the next tile's gather rows (projected rows, upstream gradient row) into L2 early
-    {
-      const long long nrow = row + (long long)gridDim.x * 128;
-      if (nrow < p.rows && h == 0) {
-        const int nb = (int)(nrow / p.E);
-        const int ne = (int)(nrow - (long long)nb * p.E);
-        const int ni = p.src_d[ne], nj = p.dst_d[ne];
-        const float* nps = p.PsPd + ((size_t)nb * p.N + ni) * 256;
-        const float* npd = p.PsPd + ((size_t)nb * p.N + nj) * 256 + 128;
-        const float* ng = p.g_aggr + ((size_t)nb * p.N + nj) * p.ld_g;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(nps + k * 32));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(npd + k * 32));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(ng + k * 32));
-        }
-      }
-    }
     // ---- recompute the forward chain
-    gather_a0();
+    gather_a0(s_ij, s_fib);
     sync_all();
     mark(1);
     if (warp == 0) {  // one elected lane issues; operands are warp-uniform (no per-lane R2UR loop per MMA)
@@ -320,6 +307,30 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
         mma_commit(bar_m);
       }
       __syncwarp();
+    }
+    // in the shadow of GEMM 1: index loads of the next tile's rows (stage 1) and the L2 prefetch of its rows
+    int2 nij = make_int2(-1, -1);
+    int nbatch = 0;
+    if (tid < 128) {
+      const long long nrow_ = (long long)(tile + gridDim.x) * 128 + tid;
+      if (tile + (int)gridDim.x < p.ntiles && nrow_ < p.rows) {
+        nbatch = (int)(nrow_ / p.E);
+        const int e_ = (int)(nrow_ - (long long)nbatch * p.E);
+        nij = make_int2(p.src_d[e_], p.dst_d[e_]);
+      }
+    }
+    {
+      if (nij.x >= 0) {
+        const float* nps = p.PsPd + ((size_t)nbatch * p.N + nij.x) * 256;
+        const float* npd = p.PsPd + ((size_t)nbatch * p.N + nij.y) * 256 + 128;
+        const float* ng = p.g_aggr + ((size_t)nbatch * p.N + nij.y) * p.ld_g;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nps + k * 32));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(npd + k * 32));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ng + k * 32));
+        }
+      }
     }
     wait_mma();
     mark(2);
@@ -333,6 +344,15 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       }
       __syncwarp();
     }
+    // in the shadow of GEMM 2: position loads of the next tile's end points (stage 2)
+    float npi[3] = {0.f, 0.f, 0.f}, npj[3] = {0.f, 0.f, 0.f};
+    if (nij.x >= 0) {
+      const float* pb = p.pos + (p.pos_batched ? (size_t)nbatch * p.N * p.P : 0);
+      for (int k = 0; k < p.P; ++k) {
+        npi[k] = pb[(size_t)nij.x * p.P + k];
+        npj[k] = pb[(size_t)nij.y * p.P + k];
+      }
+    }
     wait_mma();
     mark(4);
     act_epilogue(s_bias + 256, s_T[2], m2);
@@ -344,6 +364,22 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
         mma_commit(bar_m);
       }
       __syncwarp();
+    }
+    if (tid < 128) {  // in the shadow of GEMM 3: fiber of the next tile's row -> the other metadata buffer (stage 3)
+      float fib_[4] = {0.f, 0.f, 0.f, 0.f};
+      int2 ij = make_int2(-1, -1);
+      if (nij.x >= 0) {
+        float nrm = 0.f;
+        for (int k = 0; k < p.P; ++k) {
+          const float dlt = npi[k] - npj[k];
+          fib_[k] = dlt;
+          nrm += dlt * dlt;
+        }
+        fib_[p.P] = sqrtf(nrm);
+        ij = make_int2(nbatch * p.N + nij.x, nbatch * p.N + nij.y);
+      }
+      s_fib2[((it + 1) & 1) * 128 + tid] = make_float4(fib_[0], fib_[1], fib_[2], fib_[3]);
+      s_ij2[((it + 1) & 1) * 128 + tid] = ij;
     }
     // upstream gradient row g_aggr[dst] (this thread's 64 channels): issued before the MMA wait
     float g[64];
@@ -555,8 +591,8 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-// alignment slack + 3 weight slots + 3 tiles + s_bias[512] + s_F[128] + s_fib[128] + s_x[2][128] + s_ij[128] + 3 barriers + TMEM address
-size_t edge_chain_bwd_smem() { return 1024 + 6 * kWBlk + 512 * 4 + 128 * 16 * 2 + 256 * 16 + 128 * 8 + 3 * 8 + 16 + 128; }
+// alignment slack + 3 weight slots + 3 tiles + s_bias[512] + s_F[128] + s_fib[2][128] + s_x[2][128] + s_ij[2][128] + 3 barriers + TMEM address
+size_t edge_chain_bwd_smem() { return 1024 + 6 * kWBlk + 512 * 4 + 128 * 16 * 3 + 256 * 16 + 256 * 8 + 3 * 8 + 16 + 128; }
 
 // Fused bf16 backward of the edge stage.  gPsPd must be zero-filled; gW/gb/gW1 are accumulated into.
 int edge_chain_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const bsms_gmp_grads* gr, const float* PsPd,
