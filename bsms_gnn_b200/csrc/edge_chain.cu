@@ -2,22 +2,19 @@
 // 3 x (128x128x128 UMMA + bias [+ReLU]) -> LayerNorm -> segmented sum over dst-sorted rows ->
 // red.add into aggr.  No per-edge tensor ever reaches HBM.   (reference: src/ops/basic.py:66-94)
 //
-// CTA = 256 threads = 2 warpgroups; each warpgroup owns one 128-edge tile at a time (thread = edge
-// row = TMEM lane) with a private TMEM region [D 128 cols | A_hi 64 | A_lo 64 / ones], so the two
-// tiles ping-pong: one warpgroup's CUDA-core epilogue overlaps the other's MMAs.  Activations never
-// leave TMEM between layers (tcgen05.ld -> ReLU/convert in registers -> tcgen05.st as the next A
-// operand, TS-form MMA); the three weight matrices are staged ONCE per CTA into shared memory by
-// cp.async.bulk (pre-packed in the 128B-swizzled K-major UMMA layout) and stay resident for the
-// whole persistent loop.
-//
-// NSPLIT = 1: bf16 operands (BSMS_MODE_BF16).  The biases ride in the MMA: a constant "ones" A
-// operand (K = 16, first column 1) times a [bias | 0] B block initialises the accumulator, so the
-// epilogues are a bare ReLU + convert.
-// NSPLIT = 2: fp16 hi/lo split of both operands, 3 MMAs per K step into one fp32 accumulator
-// (BSMS_MODE_FP16X3): x ~ hi + lo with 22 significant bits, the dropped lo*lo term is 2^-22 relative —
-// the fp32-parity mode.  Operands are pre-scaled by exact powers of two (activations 2^4, weights
-// 2^8) so the lo parts stay in fp16's normal range; the accumulator is rescaled by 2^-12 and the
-// fp32 bias added in the epilogue.
+// Two kernels, one per tensor-core mode:
+//   k_edge_chain_ws  BSMS_MODE_BF16: bf16 operands, warp-specialised (8 producer warps gather row-cooperatively
+//                    into a ring of shared-memory a0 tiles, 2 consumer warpgroups run the MMA chain, LayerNorm and
+//                    the segmented reduce).  The biases ride in the MMA: a constant "ones" A operand (K = 16,
+//                    first column 1) times a [bias | 0] B block initialises the accumulator.
+//   k_edge_chain_x3  BSMS_MODE_FP16X3, the fp32-parity mode: fp16 hi/lo split of both operands, 3 MMAs per K step
+//                    into one fp32 accumulator: x ~ hi + lo with 22 significant bits, the dropped lo*lo term is
+//                    2^-22 relative.  Operands are pre-scaled by exact powers of two (activations 2^4, weights 2^8)
+//                    so the lo parts stay in fp16's normal range; the accumulator is rescaled by 2^-12 and the
+//                    fp32 bias added in the epilogue.
+// In both, thread = edge row = TMEM lane in the consumer phases, activations stay in TMEM between layers
+// (tcgen05.ld -> ReLU/convert in registers -> tcgen05.st as the next A operand, TS-form MMA), and the weight
+// images are staged ONCE per CTA by cp.async.bulk (pre-packed in the 128B-swizzled K-major UMMA layout).
 //
 // PsPd holds the per-node projections with b1 already folded into the Pd half.
 #include <stdlib.h>
@@ -37,8 +34,8 @@ struct EdgeChainParams {
   const int32_t* dst_d;
   const float* W1;  // mlp_edge layer 0 weight [128, 2*128+P+1] (fiber columns are read from it)
   const float* b[4];
-  const uint8_t* wpack;  // [3][NSPLIT] packed blocks
-  const uint8_t* bpack;  // [3] packed bias blocks (bf16 mode)
+  const uint8_t* wpack;  // packed weight images: W2, W3, W4 (bf16) or their hi, lo pairs (fp16x3)
+  const uint8_t* bpack;  // the shared bias block of the bf16 mode (k_pack_bias3)
   float* aggr;           // [B*N, 128], zero-initialised
   int B, N, E;
   long long rows;
@@ -48,68 +45,52 @@ struct EdgeChainParams {
   unsigned long long* prof;  // optional [16] per-phase cycle counters of warpgroup 0 (BSMS_PHASE_PROF=1)
 };
 
-// b2..b4 -> three 16 KB blocks in the K-major SW128 image: element (n, k=0) = bias[n], rest 0
-__global__ void k_pack_bias(const float* b2, const float* b3, const float* b4, uint8_t* __restrict__ out) {
-  const float* b = blockIdx.x == 0 ? b2 : (blockIdx.x == 1 ? b3 : b4);
-  uint8_t* o = out + (size_t)blockIdx.x * kBiasBlk;
-  for (int i = threadIdx.x; i < (int)kBiasBlk / 16; i += blockDim.x) reinterpret_cast<uint4*>(o)[i] = make_uint4(0, 0, 0, 0);
-  __syncthreads();
-  for (int n = threadIdx.x; n < 128; n += blockDim.x)
-    *reinterpret_cast<__nv_bfloat16*>(o + wblk_offset(n, 0)) = __float2bfloat16_rn(b[n]);
-}
-
-template <int NSPLIT>
-__device__ __forceinline__ void store_act32(uint32_t a_tmem, int c0, const float (&v)[32]) {
-  // 32 fp32 values of this thread's row (channels c0..c0+31) -> 16 packed columns of A (hi [, lo])
+// 32 fp32 values of this thread's row (channels c0..c0+31) -> 16 packed bf16 columns of the TMEM A operand
+__device__ __forceinline__ void store_act32_bf16(uint32_t a_tmem, int c0, const float (&v)[32]) {
   uint32_t hi[16];
-  if (NSPLIT == 1) {
 #pragma unroll
-    for (int t = 0; t < 16; ++t) hi[t] = pack_bf16(v[2 * t], v[2 * t + 1]);
-    tmem_st16(a_tmem + (c0 >> 1), hi);
-  } else {
-    uint32_t lo[16];
+  for (int t = 0; t < 16; ++t) hi[t] = pack_bf16(v[2 * t], v[2 * t + 1]);
+  tmem_st16(a_tmem + (c0 >> 1), hi);
+}
+// ... -> 16 + 16 packed fp16 columns (hi | lo halves of the scaled value) of the TMEM A operand
+__device__ __forceinline__ void store_act32_x3(uint32_t a_tmem, int c0, const float (&v)[32]) {
+  uint32_t hi[16], lo[16];
 #pragma unroll
-    for (int t = 0; t < 16; ++t) {
-      float s0 = v[2 * t] * kActScale, s1 = v[2 * t + 1] * kActScale;
-      __half h0 = __float2half_rn(s0), h1 = __float2half_rn(s1);
-      __half l0 = __float2half_rn(s0 - __half2float(h0)), l1 = __float2half_rn(s1 - __half2float(h1));
-      hi[t] = pack_f16(h0, h1);
-      lo[t] = pack_f16(l0, l1);
-    }
-    tmem_st16(a_tmem + (c0 >> 1), hi);
-    tmem_st16(a_tmem + 64 + (c0 >> 1), lo);
+  for (int t = 0; t < 16; ++t) {
+    float s0 = v[2 * t] * kActScale, s1 = v[2 * t + 1] * kActScale;
+    __half h0 = __float2half_rn(s0), h1 = __float2half_rn(s1);
+    __half l0 = __float2half_rn(s0 - __half2float(h0)), l1 = __float2half_rn(s1 - __half2float(h1));
+    hi[t] = pack_f16(h0, h1);
+    lo[t] = pack_f16(l0, l1);
   }
+  tmem_st16(a_tmem + (c0 >> 1), hi);
+  tmem_st16(a_tmem + 64 + (c0 >> 1), lo);
 }
 
-template <int NSPLIT, int CH>
-__global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) {
+// ------------------------------------------------------------------------------------------
+// k_edge_chain_x3: the fp32-parity mode (BSMS_MODE_FP16X3).  256 threads = 2 warpgroups, each owning one
+// 128-edge tile at a time (thread = edge row = TMEM lane, private TMEM [D 128 | A_hi 64 | A_lo 64]); the
+// two tiles ping-pong.  All three layers are TS-form (the 192 KB of split weights leave no room for a
+// shared-memory a0 ring), 3 MMAs per K step: hi*hi + lo*hi + hi*lo into one fp32 accumulator.
+constexpr int kX3Ch = 16;  // channels per pass of the segmented reduce: 2 row groups of 16 rows per warp
+
+__global__ void __launch_bounds__(256, 1) k_edge_chain_x3(const EdgeChainParams p) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr int NW = 3 * NSPLIT;
-  constexpr bool BIAS_MMA = (NSPLIT == 1);
-  constexpr bool COOP = (NSPLIT == 1);  // row-cooperative (coalesced) gather into a shared-memory a0 tile
-  constexpr uint32_t FMT = (NSPLIT == 1) ? 1u : 0u;  // bf16 : f16
-  constexpr uint32_t IDESC = make_idesc(FMT, 128, 128);
-  constexpr float OUT_SCALE = (NSPLIT == 1) ? 1.f : 1.f / (kActScale * kWScale);
+  constexpr int CH = kX3Ch;
+  constexpr int NW = 6;                                    // W2..W4, hi and lo images
+  constexpr uint32_t IDESC = make_idesc(0, 128, 128);      // f16 operands, f32 accumulate
+  constexpr float OUT_SCALE = 1.f / (kActScale * kWScale);
   constexpr int G = 32 / CH;   // row groups per warp in the segmented reduce
   constexpr int RPG = 32 / G;  // rows per group
   const uint32_t s0 = smem_u32(smem_raw);
   const uint32_t sbase = (s0 + 1023u) & ~1023u;
   uint8_t* sp = smem_raw + (sbase - s0);
-  const uint32_t bias_blk = sbase + NW * kWBlk;                       // 3 x 16 KB (bf16 mode only)
-  // bf16 mode: one 32 KB a0 operand tile per warpgroup (row-cooperative gather, SS-form first MMA); the
-  // segmented-reduce staging of the same warpgroup aliases it (a0 is dead once the first MMA completes)
-  const uint32_t a0_blk = bias_blk + 3 * kBiasBlk;
-  uint8_t* s_a0 = sp + NW * kWBlk + 3 * kBiasBlk;
-  uint8_t* sp2 = sp + NW * kWBlk + (BIAS_MMA ? 3 * kBiasBlk : 0) + (COOP ? 2 * kWBlk : 0);
-  float* s_bias = reinterpret_cast<float*>(sp2);         // [3][128]: b2, b3, b4 (fp16x3 mode)
-  float4* s_F = reinterpret_cast<float4*>(s_bias + 384);  // [128]
-  float4* s_fib = s_F + 128;                              // [256] fiber of each tile row (bf16 mode)
-  int2* s_ij = reinterpret_cast<int2*>(s_fib + 256);      // [256] (b*N+src, b*N+dst) of each tile row
-  float* s_stage = reinterpret_cast<float*>(s_ij + 256);  // [8][32][CH+1] (fp16x3 mode)
-  int* s_tgt = reinterpret_cast<int*>(s_stage + (COOP ? 0 : 8 * 32 * (CH + 1)));
+  float* s_bias = reinterpret_cast<float*>(sp + NW * kWBlk);  // [3][128]: b2, b3, b4
+  float4* s_F = reinterpret_cast<float4*>(s_bias + 384);       // [128] fiber coefficients of every channel
+  float* s_stage = reinterpret_cast<float*>(s_F + 128);        // [8][32][CH+1]
+  int* s_tgt = reinterpret_cast<int*>(s_stage + 8 * 32 * (CH + 1));
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tgt + 256);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 3);
-  unsigned long long* s_prof = reinterpret_cast<unsigned long long*>(s_tmem + 2);  // [16]
 
   const int tid = threadIdx.x, warp = (int)uniform(threadIdx.x >> 5), lane = tid & 31;
   const int wg = warp >> 2, tw = tid & 127, q = warp & 3;
@@ -124,57 +105,29 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
   }
   if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
   for (int i = tid; i < 384; i += 256) s_bias[i] = p.b[1 + (i >> 7)][i & 127];
-  {
+  if (tid < 128) {
     const int ldw1 = 2 * kD + p.P + 1;
-    for (int c = tid; c < 128; c += 256) {
-      float f[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int k = 0; k <= p.P; ++k) f[k] = p.W1[(size_t)c * ldw1 + k];
-      s_F[c] = make_float4(f[0], f[1], f[2], f[3]);
-    }
+    float f[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k <= p.P; ++k) f[k] = p.W1[(size_t)tid * ldw1 + k];
+    s_F[tid] = make_float4(f[0], f[1], f[2], f[3]);
   }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = uniform(*s_tmem);
   if (tid == 0) {
-    mbar_expect_tx(bar_w, NW * kWBlk + (BIAS_MMA ? 3 * kBiasBlk : 0));
+    mbar_expect_tx(bar_w, NW * kWBlk);
     for (int blk = 0; blk < NW; ++blk) bulk_g2s(sbase + blk * kWBlk, p.wpack + (size_t)blk * kWBlk, kWBlk, bar_w);
-    if (BIAS_MMA)
-      for (int l = 0; l < 3; ++l) bulk_g2s(bias_blk + l * kBiasBlk, p.bpack + (size_t)l * kBiasBlk, kBiasBlk, bar_w);
   }
   const uint32_t d_tmem = tmem_base + wg * 256;
   const uint32_t a_tmem = d_tmem + 128;
-  const uint32_t ones_tmem = d_tmem + 192;  // bf16 mode: 16 columns, element k=0 is 1.0
   const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-  if (BIAS_MMA) {
-    uint32_t ones[16];
-#pragma unroll
-    for (int t = 0; t < 16; ++t) ones[t] = 0u;
-    ones[0] = 0x00003F80u;  // bf16 pair (1.0, 0.0)
-    tmem_st16(ones_tmem + lane_off, ones);
-  }
   uint32_t phase = 0;
   bool weights_ready = false;
-  float* stage = COOP ? reinterpret_cast<float*>(s_a0 + wg * kWBlk) + q * 32 * (CH + 1) : s_stage + warp * 32 * (CH + 1);
+  float* stage = s_stage + warp * 32 * (CH + 1);
   int* tgt = s_tgt + warp * 32;
-  float4 Fl[4];  // fiber coefficients of this lane's 4 channels (row-cooperative gather)
-#pragma unroll
-  for (int c = 0; c < 4; ++c) Fl[c] = s_F[4 * lane + c];
 
-  long long tprev = 0;
-  if (false && tid == 0) {
-    for (int k = 0; k < 16; ++k) s_prof[k] = 0ull;
-    tprev = clock64();
-  }
-  auto mark = [&](int k) {
-    if (false && tid == 0) {
-      const long long t = clock64();
-      s_prof[k] += (unsigned long long)(t - tprev);
-      tprev = t;
-    }
-  };
   for (int tile = blockIdx.x * 2 + wg; tile < p.ntiles; tile += gridDim.x * 2) {
-    mark(0);
     const long long row = (long long)tile * 128 + tw;
     const bool valid = row < p.rows;
     int b = 0, i = 0, j = 0;
@@ -203,55 +156,45 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
       }
       fib[p.P] = sqrtf(nrm);
     }
-    if constexpr (COOP) {
-      // the staging region of the previous tile's segmented reduce aliases the a0 tile
-      bar_sync(1 + wg, 128);
-      s_ij[wg * 128 + tw] = valid ? make_int2(b * p.N + i, b * p.N + j) : make_int2(-1, -1);
-      s_fib[wg * 128 + tw] = make_float4(fib[0], fib[1], fib[2], fib[3]);
-      __syncwarp();
-      coop_gather_a0<8>(p.PsPd, s_ij + wg * 128, s_fib + wg * 128, Fl, s_a0 + wg * kWBlk, q * 32, q * 32 + 32, lane,
-                        p.dbg_stage == 0 ? p.dbg : nullptr, (long long)tile * 128);
-      fence_proxy_async();
-    } else {
+    {
       const float* ps_row = p.PsPd + ((size_t)b * p.N + i) * 256;
       const float* pd_row = p.PsPd + ((size_t)b * p.N + j) * 256 + 128;
       float4 ga[8], gd[8];
       const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  #pragma unroll
+#pragma unroll
       for (int q4 = 0; q4 < 8; ++q4) {
         ga[q4] = valid ? ld4(ps_row + q4 * 4) : z4;
         gd[q4] = valid ? ld4(pd_row + q4 * 4) : z4;
       }
-  #pragma unroll
+#pragma unroll
       for (int c0 = 0; c0 < 128; c0 += 32) {
         float v[32];
-  #pragma unroll
+#pragma unroll
         for (int q4 = 0; q4 < 8; ++q4) {
           v[q4 * 4 + 0] = ga[q4].x + gd[q4].x; v[q4 * 4 + 1] = ga[q4].y + gd[q4].y;
           v[q4 * 4 + 2] = ga[q4].z + gd[q4].z; v[q4 * 4 + 3] = ga[q4].w + gd[q4].w;
         }
         if (c0 + 32 < 128) {
-  #pragma unroll
+#pragma unroll
           for (int q4 = 0; q4 < 8; ++q4) {
             ga[q4] = valid ? ld4(ps_row + c0 + 32 + q4 * 4) : z4;
             gd[q4] = valid ? ld4(pd_row + c0 + 32 + q4 * 4) : z4;
           }
         }
-  #pragma unroll
+#pragma unroll
         for (int t = 0; t < 32; ++t) {
           float4 f = s_F[c0 + t];
           float x = v[t] + f.x * fib[0] + f.y * fib[1] + f.z * fib[2] + f.w * fib[3];
           v[t] = fmaxf(x, 0.f);
         }
         if (p.dbg && p.dbg_stage == 0 && valid) {
-  #pragma unroll
+#pragma unroll
           for (int t = 0; t < 32; ++t) p.dbg[row * 128 + c0 + t] = v[t];
         }
-        store_act32<NSPLIT>(a_tmem + lane_off, c0, v);
+        store_act32_x3(a_tmem + lane_off, c0, v);
       }
     }
-    // ---- pull the NEXT tile's projected rows into L2 while this tile computes (half of the gathers
-    //      miss L2 otherwise: lts hit rate 48 % under ncu), 16 x 128 B lines per thread
+    // ---- pull the NEXT tile's projected rows into L2 while this tile computes, 16 x 128 B lines per thread
     {
       const long long nrow = row + (long long)gridDim.x * 2 * 128;
       if (nrow < p.rows) {
@@ -266,14 +209,12 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
         }
       }
     }
-    mark(1);
     // ---- three UMMA layers
 #pragma unroll 1
     for (int layer = 0; layer < 3; ++layer) {
       wait_st();
       fence_before_sync();
       bar_sync(1 + wg, 128);
-      mark(2 + 3 * layer);
       if (q == 0) {  // the first warp of the warpgroup issues: one elected lane, operands warp-uniform
         if (!weights_ready) {
           mbar_wait(bar_w, 0);
@@ -281,22 +222,15 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
         }
         fence_after_sync();
         if (elect_one()) {
-          const uint32_t wb = sbase + layer * NSPLIT * kWBlk;
-          if (BIAS_MMA)  // D = ones x [bias | 0]^T
-            mma_ts(d_tmem, ones_tmem, smem_desc_sw128(bias_blk + layer * kBiasBlk, 16, 1024), IDESC, 0);
+          const uint32_t wb = sbase + layer * 2 * kWBlk;
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
             const uint32_t koff = (ks >> 2) * 16384 + (ks & 3) * 32;
             const uint64_t bhi = smem_desc_sw128(wb + koff, 16, 1024);
-            if (COOP && layer == 0)
-              mma_ss(d_tmem, smem_desc_sw128(a0_blk + wg * kWBlk + koff, 16, 1024), bhi, IDESC, 1u);
-            else
-              mma_ts(d_tmem, a_tmem + ks * 8, bhi, IDESC, (BIAS_MMA || ks > 0) ? 1u : 0u);
-            if (NSPLIT == 2) {
-              const uint64_t blo = smem_desc_sw128(wb + kWBlk + koff, 16, 1024);
-              mma_ts(d_tmem, a_tmem + 64 + ks * 8, bhi, IDESC, 1);
-              mma_ts(d_tmem, a_tmem + ks * 8, blo, IDESC, 1);
-            }
+            const uint64_t blo = smem_desc_sw128(wb + kWBlk + koff, 16, 1024);
+            mma_ts(d_tmem, a_tmem + ks * 8, bhi, IDESC, ks > 0 ? 1u : 0u);
+            mma_ts(d_tmem, a_tmem + 64 + ks * 8, bhi, IDESC, 1);
+            mma_ts(d_tmem, a_tmem + ks * 8, blo, IDESC, 1);
           }
           mma_commit(bar_m);
         }
@@ -305,7 +239,6 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
       mbar_wait(bar_m, phase);
       phase ^= 1;
       fence_after_sync();
-      mark(3 + 3 * layer);
       const float* bias = s_bias + layer * 128;
       if (layer < 2) {
 #pragma unroll 1
@@ -315,17 +248,13 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
           wait_ld();
           float v[32];
 #pragma unroll
-          for (int t = 0; t < 32; ++t) {
-            const float x = BIAS_MMA ? __uint_as_float(r[t]) : fmaf(__uint_as_float(r[t]), OUT_SCALE, bias[c0 + t]);
-            v[t] = fmaxf(x, 0.f);
-          }
+          for (int t = 0; t < 32; ++t) v[t] = fmaxf(fmaf(__uint_as_float(r[t]), OUT_SCALE, bias[c0 + t]), 0.f);
           if (p.dbg && p.dbg_stage == layer + 1 && valid) {
 #pragma unroll
             for (int t = 0; t < 32; ++t) p.dbg[row * 128 + c0 + t] = v[t];
           }
-          store_act32<NSPLIT>(a_tmem + lane_off, c0, v);
+          store_act32_x3(a_tmem + lane_off, c0, v);
         }
-        mark(4 + 3 * layer);
       } else {
         // ---- final: LayerNorm over the row.  Pass 1: shifted sums (shift = first element, so the
         //      one-pass variance has no cancellation); pass 2: normalise + segmented reduce by dst.
@@ -335,11 +264,10 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
           uint32_t r[32];
           tmem_ld32(d_tmem + lane_off + c0, r);
           wait_ld();
-          if (c0 == 0) shift = BIAS_MMA ? __uint_as_float(r[0]) : fmaf(__uint_as_float(r[0]), OUT_SCALE, bias[0]);
+          if (c0 == 0) shift = fmaf(__uint_as_float(r[0]), OUT_SCALE, bias[0]);
 #pragma unroll
           for (int t = 0; t < 32; ++t) {
-            const float y = BIAS_MMA ? __uint_as_float(r[t]) : fmaf(__uint_as_float(r[t]), OUT_SCALE, bias[c0 + t]);
-            const float dlt = y - shift;
+            const float dlt = fmaf(__uint_as_float(r[t]), OUT_SCALE, bias[c0 + t]) - shift;
             sum += dlt;
             ssq = fmaf(dlt, dlt, ssq);
           }
@@ -348,106 +276,58 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain(const EdgeChainParams p) 
         const float var = fmaxf(ssq * (1.f / 128.f) - mean_d * mean_d, 0.f);
         const float rstd = 1.f / sqrtf(var + 1e-5f);
         const float mean = shift + mean_d;
-        mark(10);
-        if constexpr (COOP) {
-          // Pass 2, row-cooperative: the warp's 32 normalised rows go through its private 8 KB of the
-          // (dead) a0 tile, 64 channels at a time ([32][64] fp32, 16-byte chunks XOR-swizzled by row);
-          // then each half-warp walks 16 of the dst-sorted rows with lane = 4 channels and flushes every
-          // finished run of equal destination with ONE 16-byte red.add per lane (256 B per half-warp).
-          float* wstage = reinterpret_cast<float*>(s_a0 + wg * kWBlk + q * 8192);
-          const int l16 = lane & 15, hw = lane >> 4;
+        const int ch = lane % CH, grp = lane / CH;
+        const uint32_t gm = (startmask >> (grp * RPG)) | 1u;
 #pragma unroll 1
-          for (int half = 0; half < 2; ++half) {
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(d_tmem + lane_off + c0, r);
+          wait_ld();
+          if (p.dbg && p.dbg_stage == 3 && valid) {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) p.dbg[row * 128 + c0 + t] = fmaf(__uint_as_float(r[t]), OUT_SCALE, bias[c0 + t]);
+          }
+#pragma unroll
+          for (int sub = 0; sub < 32; sub += CH) {
             __syncwarp();
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              uint32_t r[32];
-              tmem_ld32(d_tmem + lane_off + 64 * half + 32 * cc, r);
-              wait_ld();
-              if (p.dbg && p.dbg_stage == 3 && valid) {
-#pragma unroll
-                for (int t = 0; t < 32; ++t) p.dbg[row * 128 + 64 * half + 32 * cc + t] = __uint_as_float(r[t]);
-              }
-#pragma unroll
-              for (int q4 = 0; q4 < 8; ++q4) {
-                const float4 o = make_float4((__uint_as_float(r[4 * q4 + 0]) - mean) * rstd, (__uint_as_float(r[4 * q4 + 1]) - mean) * rstd,
-                                             (__uint_as_float(r[4 * q4 + 2]) - mean) * rstd, (__uint_as_float(r[4 * q4 + 3]) - mean) * rstd);
-                *reinterpret_cast<float4*>(wstage + lane * 64 + (((8 * cc + q4) ^ (lane & 15)) << 2)) = o;
-              }
+            for (int t = 0; t < CH; ++t) {
+              const float y = fmaf(__uint_as_float(r[sub + t]), OUT_SCALE, bias[c0 + sub + t]);
+              stage[lane * (CH + 1) + t] = (y - mean) * rstd;
             }
             __syncwarp();
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            int cur = -1;
-            float* dstc = p.aggr + 64 * half + 4 * l16;
-#pragma unroll 4
-            for (int k = 0; k < 16; ++k) {
-              const int rr = 16 * hw + k;
-              const float4 m = *reinterpret_cast<const float4*>(wstage + rr * 64 + ((l16 ^ k) << 2));
-              if (k == 0 || ((startmask >> rr) & 1u)) {
-                if (cur >= 0) red_add_v4(dstc + (size_t)cur * 128, acc.x, acc.y, acc.z, acc.w);
-                cur = tgt[rr];
+            // lanes own channels now and walk the rows of their group; a set bit in gm starts a new
+            // destination: flush the finished run with one red.add per channel
+            float* dstc = p.aggr + c0 + sub + ch;
+            const float* col = stage + (grp * RPG) * (CH + 1) + ch;
+            float acc = col[0];
+            int cur = tgt[grp * RPG];
+#pragma unroll
+            for (int rl = 1; rl < RPG; ++rl) {
+              const float m = col[rl * (CH + 1)];
+              if ((gm >> rl) & 1u) {
+                if (cur >= 0) atomicAdd(dstc + (size_t)cur * 128, acc);
+                cur = tgt[grp * RPG + rl];
                 acc = m;
               } else {
-                acc.x += m.x; acc.y += m.y; acc.z += m.z; acc.w += m.w;
+                acc += m;
               }
             }
-            if (cur >= 0) red_add_v4(dstc + (size_t)cur * 128, acc.x, acc.y, acc.z, acc.w);
-          }
-        } else {
-          const int ch = lane % CH, grp = lane / CH;
-          const uint32_t gm = (startmask >> (grp * RPG)) | 1u;
-  #pragma unroll 1
-          for (int c0 = 0; c0 < 128; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(d_tmem + lane_off + c0, r);
-            wait_ld();
-            if (p.dbg && p.dbg_stage == 3 && valid) {
-  #pragma unroll
-              for (int t = 0; t < 32; ++t)
-                p.dbg[row * 128 + c0 + t] = BIAS_MMA ? __uint_as_float(r[t]) : fmaf(__uint_as_float(r[t]), OUT_SCALE, bias[c0 + t]);
-            }
-  #pragma unroll
-            for (int sub = 0; sub < 32; sub += CH) {
-              __syncwarp();
-  #pragma unroll
-              for (int t = 0; t < CH; ++t) {
-                const float y = BIAS_MMA ? __uint_as_float(r[sub + t])
-                                         : fmaf(__uint_as_float(r[sub + t]), OUT_SCALE, bias[c0 + sub + t]);
-                stage[lane * (CH + 1) + t] = (y - mean) * rstd;
-              }
-              __syncwarp();
-              // lanes own channels now and walk the rows of their group; a set bit in gm starts a new
-              // destination: flush the finished run with one red.add per channel (128 B per warp)
-              float* dstc = p.aggr + c0 + sub + ch;
-              const float* col = stage + (grp * RPG) * (CH + 1) + ch;
-              float acc = col[0];
-              int cur = tgt[grp * RPG];
-  #pragma unroll
-              for (int rl = 1; rl < RPG; ++rl) {
-                const float m = col[rl * (CH + 1)];
-                if ((gm >> rl) & 1u) {
-                  if (cur >= 0) atomicAdd(dstc + (size_t)cur * 128, acc);
-                  cur = tgt[grp * RPG + rl];
-                  acc = m;
-                } else {
-                  acc += m;
-                }
-              }
-              if (cur >= 0) atomicAdd(dstc + (size_t)cur * 128, acc);
-            }
+            if (cur >= 0) atomicAdd(dstc + (size_t)cur * 128, acc);
           }
         }
         __syncwarp();
       }
     }
   }
-  mark(11);
-  if (false && tid == 0)
-    for (int k = 0; k < 16; ++k) atomicAdd(p.prof + k, s_prof[k]);
   // teardown
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+static size_t edge_chain_x3_smem() {
+  return 1024 + 6 * kWBlk + 384 * 4 + 128 * 16 + 8 * 32 * (kX3Ch + 1) * 4 + 256 * 4 + 3 * 8 + 16;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -668,7 +548,7 @@ __global__ void __launch_bounds__(512, 1) k_edge_chain_ws(const EdgeChainParams 
 #pragma unroll
               for (int t = 0; t < 32; ++t) p.dbg[row * 128 + c0 + t] = v[t];
             }
-            store_act32<1>(a_tmem + lane_off, c0, v);
+            store_act32_bf16(a_tmem + lane_off, c0, v);
           }
           mark(4 + 3 * layer);
         } else {
@@ -765,16 +645,10 @@ static size_t edge_chain_ws_smem() {
   return 1024 + 3 * kWBlk + kBiasBlk + kWsBuf * kWBlk + 128 * 16 + kWsBuf * 128 * (16 + 8 + 4) + 9 * 8 + 16 + 128;
 }
 
-template <int NSPLIT, int CH>
-static size_t edge_chain_smem() {
-  return 1024 + 3 * NSPLIT * kWBlk + (NSPLIT == 1 ? 3 * kBiasBlk + 2 * kWBlk : 0) + 384 * 4 + 128 * 16 + 256 * 16 + 256 * 8 +
-         (NSPLIT == 1 ? 0 : 8 * 32 * (CH + 1) * 4) + 256 * 4 + 3 * 8 + 16 + 128;
-}
-
 size_t edge_chain_pack_bytes(int mode) { return (size_t)3 * (mode == BSMS_MODE_FP16X3 ? 2 : 1) * kWBlk + 3 * kBiasBlk; }
 
 // Runs the fused edge stage.  aggr must be zero-filled by the caller; PsPd carries b1 in its Pd half.
-// wpack: [3][NSPLIT] weight blocks followed (at wpack + bias_off) by the three bias blocks (bf16).
+// wpack: the packed weight images (scratch when !prepacked); bpack: 16 KB for the shared bias block (bf16).
 int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* PsPd, const float* pos,
                        int pos_batched, int B, int P, int mode, uint8_t* wpack, float* aggr, float* dbg, int dbg_stage,
                        cudaStream_t st, bool prepacked, uint8_t* bpack) {
@@ -852,11 +726,10 @@ int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, con
       k_pack_weights<2><<<3, 256, 0, st>>>(pk, wpack);
       BSMS_LAUNCHED();
     }
-    auto kern = k_edge_chain<2, 16>;
-    const size_t smem = edge_chain_smem<2, 16>();
-    BSMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = edge_chain_x3_smem();
+    BSMS_CUDA(cudaFuncSetAttribute(k_edge_chain_x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps_(PK_EDGE_CHAIN, st);
-    kern<<<grid, 256, smem, st>>>(p);
+    k_edge_chain_x3<<<grid, 256, smem, st>>>(p);
     BSMS_LAUNCHED();
   }
   return BSMS_OK;

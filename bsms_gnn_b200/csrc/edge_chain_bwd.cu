@@ -50,24 +50,6 @@ __device__ __forceinline__ uint32_t tile_off(int r, int chunk) {  // 16-byte chu
   return (uint32_t)((chunk >> 3) * 16384 + r * 128 + (((chunk & 7) ^ (r & 7)) << 4));
 }
 
-// 64 fp32 values (channels 64h..64h+63 of row r) -> bf16 -> tile
-__device__ __forceinline__ void store_tile64(uint8_t* tile, int r, int h, const float (&v)[64]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    uint4 u;
-    u.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
-    u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-    u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-    u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-    *reinterpret_cast<uint4*>(tile + tile_off(r, 8 * h + j)) = u;
-  }
-}
-
-__device__ __forceinline__ float tile_elem(const uint8_t* tile, int r, int c) {
-  const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(tile + tile_off(r, c >> 3) + (c & 7) * 2);
-  return __bfloat162float(*p);
-}
-
 __device__ __forceinline__ void load_d64(uint32_t taddr, float (&v)[64]) {
   uint32_t r0[32], r1[32];
   tmem_ld32(taddr, r0);

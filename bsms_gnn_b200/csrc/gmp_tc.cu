@@ -27,8 +27,6 @@ int node_chain_backward(const float* Yn, const float* g_out, const float* N1, co
                         cudaStream_t st);
 WgradParams wgrad_problem(const float* G, int ldg, const float* X, int ldx, float* dW, int ldo, float* db, long long rows);
 int launch_ln_residual(const float* Yn, const float* x, const float* skip, float* out, long long rows, cudaStream_t st);
-int launch_ln_bwd_rows(const float* Y, const float* g, int ldg, float* gY, long long rows, cudaStream_t st);
-int launch_add_rows(const float* a, const float* b, int ldb, float* out, long long rows, cudaStream_t st);
 
 #define TC_TRY(expr)              \
   do {                            \
