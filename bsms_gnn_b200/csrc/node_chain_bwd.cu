@@ -119,14 +119,11 @@ __global__ void __launch_bounds__(256, 1) k_node_chain_bwd(const NodeBwdParams p
     }
     acc.x += s.x; acc.y += s.y; acc.z += s.z; acc.w += s.w;
   };
-  // rows 16w..16w+15 of X -> bf16 tile (two batches of 8 rows in flight)
+  // rows 16w..16w+15 of X -> bf16 tile (all 16 row requests of the warp in flight at once)
   auto load_tile = [&](const float* X, long long row0, uint8_t* tile) {
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      float4 v[8];
-      coop_rows_load<8>(X, kD, row0, p.rows, warp * 16 + 8 * half, lane, v);
-      coop_rows_store<8>(tile, warp * 16 + 8 * half, lane, v);
-    }
+    float4 v[16];
+    coop_rows_load<16>(X, kD, row0, p.rows, warp * 16, lane, v);
+    coop_rows_store<16>(tile, warp * 16, lane, v);
   };
   // gradient epilogue: D . [act > 0] -> the activation tile itself (in place, bf16)
   auto grad_epilogue = [&](uint8_t* tile) {
