@@ -22,9 +22,17 @@ int lin_tc2(const float* X0, int ldx0, const float* X1, int ldx1, int KB, int NB
             int ldadd1, float* Y0, int ldy0, float* Y1, int ldy1, float* ln_out, const float* res0, const float* res1,
             long long rows, int kind, cudaStream_t st);
 int wgrad_tc_batch(const WgradParams* probs, int nprob, cudaStream_t st);
-int node_chain_backward(const float* Yn, const float* g_out, const float* N1, const float* N2, const float* N3,
+int node_chain_backward(const float* Yn, const float* g_out, const float* N1, const float* N2, const float* N3, int img,
                         const uint8_t* wpack_v2, float* G4, float* const* gW, float* const* gb, long long rows,
                         cudaStream_t st);
+int node_chain_forward(const float* N1, const uint8_t* wpack_v2, const float* c2, const float* c3, const float* c4,
+                       uint8_t* img2, uint8_t* img3, float* Yn, const float* x, const float* skip, float* out,
+                       long long rows, cudaStream_t st);
+
+// The fused node chains keep N2 / N3 as bf16 operand-tile images inside the fp32-sized buffers of the node
+// tensors: ceil(Rn/128) x 32 KB fits into Rn x 512 B from 64 rows on; smaller problems (the coarsest levels of
+// small meshes) run the layer-by-layer kernels with fp32 activations.
+static inline bool node_images(long long Rn) { return Rn >= 64; }
 WgradParams wgrad_problem(const float* G, int ldg, const float* X, int ldx, float* dW, int ldo, float* db, long long rows);
 int launch_ln_residual(const float* Yn, const float* x, const float* skip, float* out, long long rows, cudaStream_t st);
 
@@ -107,6 +115,12 @@ static int forward_nodes(const bsms_level_plan* pl, const bsms_gmp_weights* w, c
       const uint8_t* b[2] = {blk(BV1A), blk(BV1B)};  // N1 = relu([x | aggr] V1^T + c1)
       TC_TRY(lin_tc2(x, kD, n.aggr, kD, 2, 1, b, 0, w->b_node[0], 1, nullptr, 0, nullptr, 0, nullptr, 0, n.N1, kD, nullptr, 0,
                      nullptr, nullptr, nullptr, Rn, K, st));
+    }
+    if (node_images(Rn)) {
+      // layers 1..3, LayerNorm and the residual(s) in one kernel; N2 / N3 are kept as operand-tile images
+      TC_TRY(node_chain_forward(n.N1, blk(BV2), w->b_node[1], w->b_node[2], w->b_node[3], reinterpret_cast<uint8_t*>(n.N2),
+                                reinterpret_cast<uint8_t*>(n.N3), n.Yn, x, skip, out, Rn, st));
+      return BSMS_OK;
     }
     const float* in[3] = {n.N1, n.N2, n.N3};
     float* o[3] = {n.N2, n.N3, n.Yn};
@@ -195,7 +209,7 @@ int gmp_backward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const 
   {
     float* gWn[3] = {gr->w_node[1], gr->w_node[2], gr->w_node[3]};
     float* gbn[3] = {gr->b_node[1], gr->b_node[2], gr->b_node[3]};
-    TC_TRY(node_chain_backward(n.Yn, g_out, n.N1, n.N2, n.N3, blk(BV2), G4, gWn, gbn, Rn, st));
+    TC_TRY(node_chain_backward(n.Yn, g_out, n.N1, n.N2, n.N3, node_images(Rn) ? 1 : 0, blk(BV2), G4, gWn, gbn, Rn, st));
   }
   {
     WgradParams pr[2] = {wgrad_problem(G4, kD, x, kD, gr->w_node[0], 2 * kD, gr->b_node[0], Rn),  // layer 0: input [x | aggr]

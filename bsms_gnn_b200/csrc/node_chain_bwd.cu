@@ -5,6 +5,8 @@
 // reference's autograd materialises every intermediate).
 //
 // Per 128-node-row tile (256 threads; row-cooperative global I/O: one warp per 512 B row):
+//   (N2, N3 arrive either as fp32 rows, converted on the way in, or — written by k_node_chain_fwd — as bf16
+//    operand-tile images that cp.async.bulk drops straight into T2 / T3)
 //   G1 = LN'(Yn) g_out                     rows of Yn, g_out  -> TG (bf16 tile)      ; N3 rows -> T3
 //   dV4 += G1^T N3 ; G2 = (G1 V4) . [N3>0]  UMMA wgrad(TG,T3), dgrad D = TG x V4(MN)  -> T3 (in place) ; N2 rows -> T2
 //   dV3 += G2^T N2 ; G3 = (G2 V3) . [N2>0]  UMMA wgrad(T3,T2), dgrad D = T3 x V3(MN)  -> T2 (in place) ; N1 rows -> TG
@@ -20,6 +22,8 @@ struct NodeBwdParams {
   const float* Yn;     // [rows,128] pre-LayerNorm output of the node MLP (kept from forward)
   const float* g_out;  // [rows,128] gradient of the block output
   const float* N[3];   // N1, N2, N3 [rows,128] (kept from forward)
+  int img;             // 1: N[1], N[2] are bf16 operand-tile images (ntiles x 32 KB, written by k_node_chain_fwd)
+                       //    and are brought in by cp.async.bulk straight into operand position
   const uint8_t* wpack;  // packed bf16 blocks V2, V3, V4 (contiguous)
   float* G4;           // [rows,128] gradient of the first layer's activation (after its ReLU mask)
   float* gW[3];        // V2, V3, V4 gradients [128,128] (accumulated)
@@ -44,17 +48,18 @@ __global__ void __launch_bounds__(256, 1) k_node_chain_bwd(const NodeBwdParams p
   uint8_t* s_T3 = sp + 4 * kWBlk;
   uint8_t* s_T2 = sp + 5 * kWBlk;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(sp + 6 * kWBlk);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 3);
   const uint32_t aV[3] = {sbase, sbase + kWBlk, sbase + 2 * kWBlk};
   const uint32_t aTG = sbase + 3 * kWBlk, aT3 = sbase + 4 * kWBlk, aT2 = sbase + 5 * kWBlk;
   float* s_stage = reinterpret_cast<float*>(s_T3);  // fp32 [128][128] over T3|T2
 
   const int tid = threadIdx.x, warp = (int)uniform(threadIdx.x >> 5), lane = tid & 31;
   const int q = warp & 3, h = warp >> 2, r = q * 32 + lane;
-  const uint32_t bar_w = smem_u32(&s_bar[0]), bar_m = smem_u32(&s_bar[1]);
+  const uint32_t bar_w = smem_u32(&s_bar[0]), bar_m = smem_u32(&s_bar[1]), bar_l = smem_u32(&s_bar[2]);
   if (tid == 0) {
     mbar_init(bar_w, 1);
     mbar_init(bar_m, 1);
+    mbar_init(bar_l, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
@@ -70,7 +75,7 @@ __global__ void __launch_bounds__(256, 1) k_node_chain_bwd(const NodeBwdParams p
   const uint32_t d_tmem = tmem_base;  // D: cols [0,128); dV2/dV3/dV4: cols [128,256), [256,384), [384,512)
   const uint32_t lane_off = (uint32_t)(q * 32) << 16;
   const uint32_t d_mine = d_tmem + lane_off + 64 * h;
-  uint32_t phase = 0, wacc = 0;
+  uint32_t phase = 0, phase_l = 0, wacc = 0;
   float4 acc_b[3];  // bias-gradient partial sums of this lane's 4 channels (c2, c3, c4)
 #pragma unroll
   for (int l = 0; l < 3; ++l) acc_b[l] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -153,6 +158,12 @@ __global__ void __launch_bounds__(256, 1) k_node_chain_bwd(const NodeBwdParams p
 
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const long long row0 = (long long)tile * 128;
+    if (p.img && tid == 0) {
+      // N3 -> T3 and N2 -> T2 as ready-made operand tiles (both slots were the previous tile's staging: free)
+      mbar_expect_tx(bar_l, 2 * kWBlk);
+      bulk_g2s(aT3, reinterpret_cast<const uint8_t*>(p.N[2]) + (size_t)tile * kWBlk, kWBlk, bar_l);
+      bulk_g2s(aT2, reinterpret_cast<const uint8_t*>(p.N[1]) + (size_t)tile * kWBlk, kWBlk, bar_l);
+    }
     // ---- G1 = LayerNorm backward of g_out through Yn (warp per row), N3 -> T3
     {
       const uint32_t col_off = (uint32_t)((lane >> 4) * 16384 + (lane & 1) * 8);
@@ -179,11 +190,16 @@ __global__ void __launch_bounds__(256, 1) k_node_chain_bwd(const NodeBwdParams p
         }
       }
     }
-    load_tile(p.N[2], row0, s_T3);
+    if (p.img) {
+      mbar_wait(bar_l, phase_l);  // the two image tiles have landed
+      phase_l ^= 1;
+    } else {
+      load_tile(p.N[2], row0, s_T3);
+    }
     sync_all();
     issue_pair(tmem_base + 384, aTG, aT3, aV[2]);  // dV4 += G1^T N3 ; D = G1 V4
     colsum(s_TG, acc_b[2]);
-    load_tile(p.N[1], row0, s_T2);                 // N2 -> T2 in the shadow of the MMAs
+    if (!p.img) load_tile(p.N[1], row0, s_T2);     // N2 -> T2 in the shadow of the MMAs
     wait_mma();
     grad_epilogue(s_T3);                           // G2 -> T3
     sync_all();
@@ -226,7 +242,7 @@ __global__ void __launch_bounds__(256, 1) k_node_chain_bwd(const NodeBwdParams p
       if (row < p.rows)
         st4(p.G4 + row * kD + 4 * lane, *reinterpret_cast<const float4*>(s_stage + rr * 128 + ((lane ^ (rr & 31)) << 2)));
     }
-    __syncthreads();  // the tiles are rewritten by the next tile
+    sync_all();  // the tiles are rewritten by the next tile (by cp.async.bulk in image mode: proxy fence included)
   }
 
   // ---- flush: weight-gradient accumulators (TMEM) and the per-lane bias partial sums
@@ -262,7 +278,7 @@ __global__ void __launch_bounds__(256, 1) k_node_chain_bwd(const NodeBwdParams p
 }
 
 // G4 = gradient of the first node layer's activation; accumulates dV2..dV4 and dc2..dc4.
-int node_chain_backward(const float* Yn, const float* g_out, const float* N1, const float* N2, const float* N3,
+int node_chain_backward(const float* Yn, const float* g_out, const float* N1, const float* N2, const float* N3, int img,
                         const uint8_t* wpack_v2, float* G4, float* const* gW, float* const* gb, long long rows,
                         cudaStream_t st) {
   if (rows == 0) return BSMS_OK;
@@ -272,6 +288,7 @@ int node_chain_backward(const float* Yn, const float* g_out, const float* N1, co
   p.N[0] = N1;
   p.N[1] = N2;
   p.N[2] = N3;
+  p.img = img;
   p.wpack = wpack_v2;
   p.G4 = G4;
   for (int l = 0; l < 3; ++l) {
@@ -283,7 +300,7 @@ int node_chain_backward(const float* Yn, const float* g_out, const float* N1, co
   int dev = 0, sms = 148;
   BSMS_CUDA(cudaGetDevice(&dev));
   BSMS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const size_t smem = 1024 + 6 * kWBlk + 2 * 8 + 16;
+  const size_t smem = 1024 + 6 * kWBlk + 3 * 8 + 16;
   BSMS_CUDA(cudaFuncSetAttribute(k_node_chain_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope ps_(PK_DGRAD, st);
   k_node_chain_bwd<<<std::min(sms, p.ntiles), 256, smem, st>>>(p);
