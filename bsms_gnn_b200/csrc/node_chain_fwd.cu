@@ -153,25 +153,36 @@ __global__ void __launch_bounds__(256, 1) k_node_chain_fwd(const NodeFwdParams p
       }
     }
     __syncthreads();
-    // ---- row-cooperative pass: Yn rows out, LayerNorm + residual(s) -> block output
-#pragma unroll 4
-    for (int rr = warp * 16; rr < warp * 16 + 16; ++rr) {
-      const long long row = row0 + rr;
-      if (row < p.rows) {
-        const float4 v = *reinterpret_cast<const float4*>(s_stage + rr * 128 + ((lane ^ (rr & 31)) << 2));
-        st4(p.Yn + row * kD + 4 * lane, v);
-        if (p.out) {
-          const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.f / 128.f);
-          const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
-          const float var = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.f / 128.f);
-          const float rstd = 1.f / sqrtf(var + 1e-5f);
-          float4 o = ld4(p.x + row * kD + 4 * lane);
-          o.x += dx * rstd; o.y += dy * rstd; o.z += dz * rstd; o.w += dw * rstd;
-          if (p.skip) {
-            const float4 s = ld4(p.skip + row * kD + 4 * lane);
-            o.x += s.x; o.y += s.y; o.z += s.z; o.w += s.w;
+    // ---- row-cooperative pass: Yn rows out, LayerNorm + residual(s) -> block output.  The residual rows of
+    //      8 tile rows are requested together (16 loads in flight per warp) before the rows are normalised:
+    //      one exposed DRAM latency per 8 rows instead of one per row
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int rb = warp * 16 + 8 * half;
+      float4 xr[8], sk[8];
+      if (p.out) {
+        coop_rows_load<8>(p.x, kD, row0, p.rows, rb, lane, xr);
+        if (p.skip) coop_rows_load<8>(p.skip, kD, row0, p.rows, rb, lane, sk);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int rr = rb + u;
+        const long long row = row0 + rr;
+        if (row < p.rows) {
+          const float4 v = *reinterpret_cast<const float4*>(s_stage + rr * 128 + ((lane ^ (rr & 31)) << 2));
+          st4(p.Yn + row * kD + 4 * lane, v);
+          if (p.out) {
+            const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.f / 128.f);
+            const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+            const float var = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.f / 128.f);
+            const float rstd = 1.f / sqrtf(var + 1e-5f);
+            float4 o = xr[u];
+            o.x += dx * rstd; o.y += dy * rstd; o.z += dz * rstd; o.w += dw * rstd;
+            if (p.skip) {
+              o.x += sk[u].x; o.y += sk[u].y; o.z += sk[u].z; o.w += sk[u].w;
+            }
+            st4(p.out + row * kD + 4 * lane, o);
           }
-          st4(p.out + row * kD + 4 * lane, o);
         }
       }
     }
