@@ -34,7 +34,7 @@ class GmpWeightsC(C.Structure):
 
 
 EXPORTS = [
-    "bsms_last_error", "bsms_version", "bsms_device_info", "bsms_plan_workspace_bytes", "bsms_plan_build",
+    "bsms_last_error", "bsms_version", "bsms_device_info", "bsms_plan_workspace_bytes", "bsms_plan_build", "bsms_fingerprint",
     "bsms_cal_ew", "bsms_permute_ew", "bsms_edge_conv", "bsms_conv_down_pool", "bsms_unpool_conv_up",
     "bsms_gather_rows", "bsms_unpool_rows", "bsms_gmp_workspace_bytes", "bsms_gmp_saved_bytes", "bsms_gmp_forward",
     "bsms_gmp_backward", "bsms_launch_count", "bsms_prof_enable", "bsms_prof_collect",
@@ -57,6 +57,7 @@ def _load():
     lib.bsms_plan_workspace_bytes.restype = sz
     lib.bsms_plan_workspace_bytes.argtypes = [i64, i64]
     lib.bsms_plan_build.argtypes = [vp, i64, i64, P(LevelPlanC), vp, vp, sz, vp]
+    lib.bsms_fingerprint.argtypes = [P(vp), P(i64), i32, vp, vp]
     lib.bsms_cal_ew.argtypes = [P(LevelPlanC), vp, vp, vp, vp, vp, vp]
     lib.bsms_permute_ew.argtypes = [P(LevelPlanC), vp, vp, vp, vp]
     lib.bsms_edge_conv.argtypes = [P(LevelPlanC), vp, vp, vp, i32, i32, i32, vp]
@@ -97,6 +98,7 @@ def ptr(t):
 
 
 def stream_ptr():
+    """cudaStream_t of torch's current stream on the CURRENT device (call inside `torch.cuda.device(dev)`)."""
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -116,8 +118,8 @@ _WS = {}
 
 def workspace(nbytes: int, device) -> torch.Tensor:
     """Grow-only scratch buffer per (device, stream) — stream-ordered reuse."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(),
-           torch.cuda.current_stream().cuda_stream)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, torch.cuda.current_stream(idx).cuda_stream)
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)

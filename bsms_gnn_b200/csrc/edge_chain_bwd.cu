@@ -62,12 +62,22 @@ __device__ __forceinline__ void load_d64(uint32_t taddr, float (&v)[64]) {
   }
 }
 
-template <bool PROF>
+// Structure notes (measured on B200, profiles/r2_bwd_*.txt):
+//  * ReLU + bf16 packing is one cvt (F2FP.RELU), ReLU masks are re-derived from the stored activation tiles
+//    (a > 0 <=> its bf16 image is non-zero), LayerNorm backward is two FMAs per element, and the
+//    weight-gradient MMA of every backward layer is issued AFTER its data-gradient MMA on its own barrier,
+//    so it runs under the epilogue of the data gradient instead of in front of it (8.66 -> 7.88 ms / step).
+//  * NS ("N-split"): every 128x128x128 GEMM is issued as two N = 64 halves with their own barriers, and every
+//    thread owns 32 channels of EACH half, so the epilogue of half 0 runs under the MMA of half 1.
+//  * F2: the epilogue arithmetic uses the packed fp32x2 instructions of sm_100 (FADD2 / FFMA2): the epilogues
+//    are bound by the FMA pipe's issue rate, not by latency.
+template <bool PROF, bool NS, bool F2>
 __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr uint32_t IDESC_KK = make_idesc(1, 128, 128, 0, 0);  // A K-major, B K-major   (recompute)
-  constexpr uint32_t IDESC_KM = make_idesc(1, 128, 128, 0, 1);  // A K-major, B MN-major  (dgrad: B = W^T)
-  constexpr uint32_t IDESC_MM = make_idesc(1, 128, 128, 1, 1);  // A, B MN-major          (wgrad)
+  constexpr uint32_t NH = NS ? 64 : 128;                          // N of one MMA group
+  constexpr uint32_t IDESC_KK = make_idesc(1, 128, NH, 0, 0);     // A K-major, B K-major   (recompute)
+  constexpr uint32_t IDESC_KM = make_idesc(1, 128, NH, 0, 1);     // A K-major, B MN-major  (dgrad: B = W^T)
+  constexpr uint32_t IDESC_MM = make_idesc(1, 128, 128, 1, 1);    // A, B MN-major          (wgrad)
   const uint32_t s0 = smem_u32(smem_raw);
   const uint32_t sbase = (s0 + 1023u) & ~1023u;
   uint8_t* sp = smem_raw + (sbase - s0);
@@ -78,18 +88,22 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
   float4* s_x = s_fib2 + 256;                                // [2][128] LayerNorm partial sums
   int2* s_ij2 = reinterpret_cast<int2*>(s_x + 256);          // [2][128] (b*N+src, b*N+dst) of each tile row, -1 past the end
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_ij2 + 256);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 3);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 5);
   const uint32_t aW[3] = {sbase, sbase + kWBlk, sbase + 2 * kWBlk};
   const uint32_t aT[3] = {sbase + 3 * kWBlk, sbase + 4 * kWBlk, sbase + 5 * kWBlk};
 
   const int tid = threadIdx.x, warp = (int)uniform(threadIdx.x >> 5), lane = tid & 31;
   const int q = warp & 3, h = warp >> 2, r = q * 32 + lane;
   const uint32_t bar_w = smem_u32(&s_bar[0]), bar_m = smem_u32(&s_bar[1]), bar_r = smem_u32(&s_bar[2]);
+  const uint32_t bar_g = smem_u32(&s_bar[3]);  // completion of the weight-gradient MMA issued behind a data-gradient MMA
+  const uint32_t bar_h = smem_u32(&s_bar[4]);  // NS: completion of the second N half
 
   if (tid == 0) {
     mbar_init(bar_w, 1);
     mbar_init(bar_m, 1);
     mbar_init(bar_r, 1);
+    mbar_init(bar_g, 1);
+    mbar_init(bar_h, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
@@ -117,8 +131,10 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
   }
   const uint32_t d_tmem = tmem_base;  // D: cols [0,128); dW2/dW3/dW4: cols [128,256), [256,384), [384,512)
   const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-  const uint32_t d_mine = d_tmem + lane_off + 64 * h;
-  uint32_t phase = 0, phase_r = 0;
+  // this thread's two groups of 32 channels (= TMEM columns of D): NS: one group in each N half
+  const int ch0[2] = {NS ? 32 * h : 64 * h, NS ? 64 + 32 * h : 64 * h + 32};
+  const uint32_t d_col[2] = {d_tmem + lane_off + (uint32_t)ch0[0], d_tmem + lane_off + (uint32_t)ch0[1]};
+  uint32_t phase = 0, phase_r = 0, phase_g = 0, phase_h = 0;
   uint8_t* s_gy = sp;  // the W2 slot: W2 is idle between the first recompute GEMM and the last data-gradient GEMM,
                        // so gy lives there meanwhile and W2 is brought back by cp.async.bulk (32 KB from L2 per tile)
   uint32_t wacc = 0;  // weight-gradient accumulators hold something
@@ -136,11 +152,10 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       tprev = t;
     }
   };
-  // persistent per-thread partial sums for the bias / fiber-weight gradients (channel cc, row half rh)
-  float4 acc_b[4];  // bias-gradient partial sums of this lane's 4 channels; [0] unused (acc_b0 below)
+  // persistent per-thread partial sums for the bias / fiber-weight gradients: lane l owns channels 4l..4l+3
+  float4 acc_b[4];  // layers 2..4 ([0] unused: acc_b0 below)
 #pragma unroll
   for (int l = 0; l < 4; ++l) acc_b[l] = make_float4(0.f, 0.f, 0.f, 0.f);
-  // row-cooperative passes: lane l owns channels 4l..4l+3
   float4 acc_b0 = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 acc_fl[4];  // [fiber component k] x 4 channels
 #pragma unroll
@@ -154,19 +169,33 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     __syncthreads();
     fence_after_sync();
   };
-  auto wait_mma = [&]() {
-    mbar_wait(bar_m, phase);
-    phase ^= 1;
-    fence_after_sync();
+  // the accumulator columns of channel group hh are complete (NS: group hh lives in N half hh)
+  auto wait_half = [&](int hh) {
+    if (hh == 0) {
+      mbar_wait(bar_m, phase);
+      phase ^= 1;
+      fence_after_sync();
+    } else if (NS) {
+      mbar_wait(bar_h, phase_h);
+      phase_h ^= 1;
+      fence_after_sync();
+    }
   };
-  // D = A(tile, K-major) x B(weight block): K-major B for the recompute, MN-major B (= W^T) for dgrad
+  // D = A(tile, K-major) x B(weight block): K-major B for the recompute, MN-major B (= W^T) for dgrad;
+  // NS: two N = 64 groups, each committed to its own barrier
   auto issue_gemm = [&](uint32_t a_tile, uint32_t b_blk, bool b_mn) {
 #pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {
-      const uint64_t ad = smem_desc_sw128(a_tile + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
-      const uint64_t bd = b_mn ? smem_desc_sw128(b_blk + ks * 2048, 16384, 1024)
-                               : smem_desc_sw128(b_blk + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
-      mma_ss(d_tmem, ad, bd, b_mn ? IDESC_KM : IDESC_KK, ks > 0);
+    for (int hn = 0; hn < (NS ? 2 : 1); ++hn) {
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t ad = smem_desc_sw128(a_tile + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
+        // K-major B: rows n of the [n][k] image, N half = +64 rows; MN-major B: N runs along the 128-byte atom,
+        // N half = the next atom (+16 KB)
+        const uint64_t bd = b_mn ? smem_desc_sw128(b_blk + hn * 16384 + ks * 2048, 16384, 1024)
+                                 : smem_desc_sw128(b_blk + (ks >> 2) * 16384 + hn * 8192 + (ks & 3) * 32, 16, 1024);
+        mma_ss(d_tmem + 64 * hn, ad, bd, b_mn ? IDESC_KM : IDESC_KK, ks > 0);
+      }
+      mma_commit(hn == 0 ? bar_m : bar_h);
     }
   };
   // dW[out][in] += G^T A : both operands MN-major views of [row][channel] tiles, K = 128 tile rows
@@ -177,6 +206,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       const uint64_t bd = smem_desc_sw128(a_tile + ks * 2048, 16384, 1024);
       mma_ss(dw_tmem, ad, bd, IDESC_MM, (wacc | ks) != 0);
     }
+    mma_commit(bar_g);
   };
   // column sums of a gradient tile (bias gradient), row-cooperative: warp w sums rows 16w..16w+15, lane l
   // owns channels 4l..4l+3 (one 8-byte shared load per row); overlaps the MMAs
@@ -197,6 +227,20 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
 #pragma unroll
     for (int c = 0; c < 4; ++c) Fl[c] = s_F[4 * lane + c];
     coop_gather_a0<8>(p.PsPd, s_ij, s_fib, Fl, s_T[0], warp * 16, warp * 16 + 16, lane, nullptr, 0);
+  };
+  // (D + bias) of 8 consecutive accumulator columns -> fp32 pairs
+  auto add_bias8 = [&](const uint32_t* rr8, const float4 ba, const float4 bb, float2 (&x)[4]) {
+    if constexpr (F2) {
+      x[0] = __fadd2_rn(make_float2(__uint_as_float(rr8[0]), __uint_as_float(rr8[1])), make_float2(ba.x, ba.y));
+      x[1] = __fadd2_rn(make_float2(__uint_as_float(rr8[2]), __uint_as_float(rr8[3])), make_float2(ba.z, ba.w));
+      x[2] = __fadd2_rn(make_float2(__uint_as_float(rr8[4]), __uint_as_float(rr8[5])), make_float2(bb.x, bb.y));
+      x[3] = __fadd2_rn(make_float2(__uint_as_float(rr8[6]), __uint_as_float(rr8[7])), make_float2(bb.z, bb.w));
+    } else {
+      x[0] = make_float2(__uint_as_float(rr8[0]) + ba.x, __uint_as_float(rr8[1]) + ba.y);
+      x[1] = make_float2(__uint_as_float(rr8[2]) + ba.z, __uint_as_float(rr8[3]) + ba.w);
+      x[2] = make_float2(__uint_as_float(rr8[4]) + bb.x, __uint_as_float(rr8[5]) + bb.y);
+      x[3] = make_float2(__uint_as_float(rr8[6]) + bb.z, __uint_as_float(rr8[7]) + bb.w);
+    }
   };
 
   int it = 0;
@@ -232,50 +276,62 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     const long long row = (long long)tile * 128 + r;
     const bool valid = row < p.rows;
     const int rowj = s_ij[r].y;
-    uint32_t m1[2] = {0u, 0u}, m2[2] = {0u, 0u};
 
-    // 32 fp32 values -> bf16 -> chunks [chunk0, chunk0+4) of row r
-    auto store32 = [&](uint8_t* tile, int chunk0, const float (&v)[32]) {
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        uint4 u;
-        u.x = pack_bf16(v[8 * jj + 0], v[8 * jj + 1]); u.y = pack_bf16(v[8 * jj + 2], v[8 * jj + 3]);
-        u.z = pack_bf16(v[8 * jj + 4], v[8 * jj + 5]); u.w = pack_bf16(v[8 * jj + 6], v[8 * jj + 7]);
-        *reinterpret_cast<uint4*>(tile + tile_off(r, chunk0 + jj)) = u;
-      }
-    };
-    // every phase handles this thread's 64 channels as two halves of 32 (register budget)
-    // activation epilogue: D + bias -> ReLU -> tile, mask
-    auto act_epilogue = [&](const float* bias, uint8_t* dst_tile, uint32_t (&mask)[2]) {
+    // activation epilogue: relu(D + bias) -> tile; ReLU rides in the bf16 conversion, no mask is kept
+    auto act_epilogue = [&](const float* bias, uint8_t* dst_tile) {
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
+        wait_half(hh);
         uint32_t rr_[32];
-        tmem_ld32(d_mine + 32 * hh, rr_);
+        tmem_ld32(d_col[hh], rr_);
         wait_ld();
-        float v[32];
-        uint32_t mk = 0u;
+        const float4* b4 = reinterpret_cast<const float4*>(bias + ch0[hh]);
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          float x = __uint_as_float(rr_[t]) + bias[64 * h + 32 * hh + t];
-          const bool on = x > 0.f;
-          v[t] = on ? x : 0.f;
-          mk |= (on ? 1u : 0u) << t;
+        for (int jj = 0; jj < 4; ++jj) {
+          float2 x[4];
+          add_bias8(rr_ + 8 * jj, b4[2 * jj], b4[2 * jj + 1], x);
+          uint4 u;
+          u.x = pack_relu_bf16(x[0].x, x[0].y);
+          u.y = pack_relu_bf16(x[1].x, x[1].y);
+          u.z = pack_relu_bf16(x[2].x, x[2].y);
+          u.w = pack_relu_bf16(x[3].x, x[3].y);
+          *reinterpret_cast<uint4*>(dst_tile + tile_off(r, (ch0[hh] >> 3) + jj)) = u;
         }
-        mask[hh] = mk;
-        store32(dst_tile, 8 * h + 4 * hh, v);
       }
     };
-    // gradient epilogue: D . mask -> tile
-    auto grad_epilogue = [&](const uint32_t (&mask)[2], uint8_t* dst_tile) {
+    // gradient epilogue: g = D . [act > 0] written IN PLACE over the activation tile `tile` (same thread, same
+    // bytes).  The weight-gradient MMA issued behind the data-gradient MMA still reads `tile` (and the gradient
+    // tile before it): the TMEM load and the arithmetic of the first group run under it, the first store waits
+    // for its barrier.
+    auto grad_epilogue = [&](uint8_t* tile) {
+      const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
+        wait_half(hh);
         uint32_t rr_[32];
-        tmem_ld32(d_mine + 32 * hh, rr_);
+        tmem_ld32(d_col[hh], rr_);
         wait_ld();
-        float v[32];
+        uint4 u[4];
 #pragma unroll
-        for (int t = 0; t < 32; ++t) v[t] = ((mask[hh] >> t) & 1u) ? __uint_as_float(rr_[t]) : 0.f;
-        store32(dst_tile, 8 * h + 4 * hh, v);
+        for (int jj = 0; jj < 4; ++jj) {
+          const uint4 a8 = *reinterpret_cast<const uint4*>(tile + tile_off(r, (ch0[hh] >> 3) + jj));
+          const uint32_t aw[4] = {a8.x, a8.y, a8.z, a8.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int w2 = 0; w2 < 4; ++w2) {
+            const uint32_t gp = pack_bf16(__uint_as_float(rr_[8 * jj + 2 * w2]), __uint_as_float(rr_[8 * jj + 2 * w2 + 1]));
+            const __nv_bfloat162 on = __hgt2(*reinterpret_cast<const __nv_bfloat162*>(&aw[w2]), z2);  // 1.0 / 0.0 per half
+            const __nv_bfloat162 gm = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&gp), on);
+            o[w2] = *reinterpret_cast<const uint32_t*>(&gm);
+          }
+          u[jj] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        if (hh == 0) {  // the weight-gradient MMA behind this data gradient has read the tile
+          mbar_wait(bar_g, phase_g);
+          phase_g ^= 1;
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) *reinterpret_cast<uint4*>(tile + tile_off(r, (ch0[hh] >> 3) + jj)) = u[jj];
       }
     };
 
@@ -284,10 +340,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     sync_all();
     mark(1);
     if (warp == 0) {  // one elected lane issues; operands are warp-uniform (no per-lane R2UR loop per MMA)
-      if (elect_one()) {
-        issue_gemm(aT[0], aW[0], false);
-        mma_commit(bar_m);
-      }
+      if (elect_one()) issue_gemm(aT[0], aW[0], false);
       __syncwarp();
     }
     // in the shadow of GEMM 1: index loads of the next tile's rows (stage 1) and the L2 prefetch of its rows
@@ -314,16 +367,12 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
         }
       }
     }
-    wait_mma();
     mark(2);
-    act_epilogue(s_bias + 128, s_T[1], m1);
+    act_epilogue(s_bias + 128, s_T[1]);
     sync_all();
     mark(3);
     if (warp == 0) {
-      if (elect_one()) {
-        issue_gemm(aT[1], aW[1], false);
-        mma_commit(bar_m);
-      }
+      if (elect_one()) issue_gemm(aT[1], aW[1], false);
       __syncwarp();
     }
     // in the shadow of GEMM 2: position loads of the next tile's end points (stage 2)
@@ -335,16 +384,12 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
         npj[k] = pb[(size_t)nij.y * p.P + k];
       }
     }
-    wait_mma();
     mark(4);
-    act_epilogue(s_bias + 256, s_T[2], m2);
+    act_epilogue(s_bias + 256, s_T[2]);
     sync_all();
     mark(5);
     if (warp == 0) {
-      if (elect_one()) {
-        issue_gemm(aT[2], aW[2], false);
-        mma_commit(bar_m);
-      }
+      if (elect_one()) issue_gemm(aT[2], aW[2], false);
       __syncwarp();
     }
     if (tid < 128) {  // in the shadow of GEMM 3: fiber of the next tile's row -> the other metadata buffer (stage 3)
@@ -363,36 +408,54 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       s_fib2[((it + 1) & 1) * 128 + tid] = make_float4(fib_[0], fib_[1], fib_[2], fib_[3]);
       s_ij2[((it + 1) & 1) * 128 + tid] = ij;
     }
-    // upstream gradient row g_aggr[dst] (this thread's 64 channels): issued before the MMA wait
-    float g[64];
+    // upstream gradient row g_aggr[dst] (this thread's 2 x 32 channels): issued before the MMA wait
+    float2 g[32];
     {
-      const float* grow = p.g_aggr + (size_t)(valid ? rowj : 0) * p.ld_g + 64 * h;
-#pragma unroll
-      for (int q4 = 0; q4 < 16; ++q4) {
-        float4 gv = valid ? ld4(grow + q4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        g[q4 * 4 + 0] = gv.x; g[q4 * 4 + 1] = gv.y; g[q4 * 4 + 2] = gv.z; g[q4 * 4 + 3] = gv.w;
-      }
-    }
-    wait_mma();
-    mark(6);
-    // ---- LayerNorm backward: gy = rstd * (g - mean(g) - yhat * mean(g * yhat)) -> T0
-    //      two sweeps over this thread's 64 accumulator columns, 32 at a time (register budget)
-    {
-      float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
+      const float* grow = p.g_aggr + (size_t)(valid ? rowj : 0) * p.ld_g;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
-        uint32_t rr_[32];
-        tmem_ld32(d_mine + 32 * hh, rr_);
-        wait_ld();
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          const float yv = __uint_as_float(rr_[t]) + s_bias[384 + 64 * h + 32 * hh + t];
-          s1 += yv;
-          s2 = fmaf(yv, yv, s2);
-          s3 += g[32 * hh + t];
-          s4 = fmaf(g[32 * hh + t], yv, s4);
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 gv = valid ? ld4(grow + ch0[hh] + q4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          g[16 * hh + 2 * q4] = make_float2(gv.x, gv.y);
+          g[16 * hh + 2 * q4 + 1] = make_float2(gv.z, gv.w);
         }
       }
+    }
+    mark(6);
+    // ---- LayerNorm backward: gy = rstd * (g - mean(g) - yhat * mean(g * yhat)) -> the W2 slot
+    //      two sweeps over this thread's 64 accumulator columns, 32 at a time (register budget)
+    {
+      float2 t1 = make_float2(0.f, 0.f), t2 = t1, t3 = t1, t4 = t1;  // even / odd partial sums of y, y^2, g, g y
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        wait_half(hh);
+        uint32_t rr_[32];
+        tmem_ld32(d_col[hh], rr_);
+        wait_ld();
+        const float4* b4 = reinterpret_cast<const float4*>(s_bias + 384 + ch0[hh]);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          float2 y[4];
+          add_bias8(rr_ + 8 * jj, b4[2 * jj], b4[2 * jj + 1], y);
+#pragma unroll
+          for (int w2 = 0; w2 < 4; ++w2) {
+            const float2 gp = g[16 * hh + 4 * jj + w2];
+            if constexpr (F2) {
+              t1 = __fadd2_rn(t1, y[w2]);
+              t2 = __ffma2_rn(y[w2], y[w2], t2);
+              t3 = __fadd2_rn(t3, gp);
+              t4 = __ffma2_rn(gp, y[w2], t4);
+            } else {
+              t1.x += y[w2].x; t1.y += y[w2].y;
+              t2.x = fmaf(y[w2].x, y[w2].x, t2.x); t2.y = fmaf(y[w2].y, y[w2].y, t2.y);
+              t3.x += gp.x; t3.y += gp.y;
+              t4.x = fmaf(gp.x, y[w2].x, t4.x); t4.y = fmaf(gp.y, y[w2].y, t4.y);
+            }
+          }
+        }
+      }
+      float s1 = t1.x + t1.y, s2 = t2.x + t2.y, s3 = t3.x + t3.y, s4 = t4.x + t4.y;
       s_x[h * 128 + r] = make_float4(s1, s2, s3, s4);
       __syncthreads();
       const float4 o = s_x[(1 - h) * 128 + r];
@@ -402,24 +465,34 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       const float rstd = 1.f / sqrtf(var + 1e-5f);
       const float c1 = s3 * (1.f / 128.f);
       const float c2 = rstd * (s4 - mean * s3) * (1.f / 128.f);
+      // rstd (g - c1 - yh c2) with yh = (y - mean) rstd  ==  kA g + kB y + kC  (two FMAs per element)
+      const float kA = valid ? rstd : 0.f;
+      const float kB = valid ? -rstd * rstd * c2 : 0.f;
+      const float kC = valid ? rstd * (rstd * c2 * mean - c1) : 0.f;
+      const float2 kA2 = make_float2(kA, kA), kB2 = make_float2(kB, kB), kC2 = make_float2(kC, kC);
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t rr_[32];
-        tmem_ld32(d_mine + 32 * hh, rr_);
+        tmem_ld32(d_col[hh], rr_);
         wait_ld();
+        const float4* b4 = reinterpret_cast<const float4*>(s_bias + 384 + ch0[hh]);
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
-          float o8[8];
+          float2 y[4];
+          add_bias8(rr_ + 8 * jj, b4[2 * jj], b4[2 * jj + 1], y);
+          uint32_t o4[4];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int t = 8 * jj + e;
-            const float yh = (__uint_as_float(rr_[t]) + s_bias[384 + 64 * h + 32 * hh + t] - mean) * rstd;
-            o8[e] = valid ? rstd * (g[32 * hh + t] - c1 - yh * c2) : 0.f;
+          for (int w2 = 0; w2 < 4; ++w2) {
+            const float2 gp = g[16 * hh + 4 * jj + w2];
+            float2 ov;
+            if constexpr (F2) {
+              ov = __ffma2_rn(kA2, gp, __ffma2_rn(kB2, y[w2], kC2));
+            } else {
+              ov = make_float2(fmaf(kA, gp.x, fmaf(kB, y[w2].x, kC)), fmaf(kA, gp.y, fmaf(kB, y[w2].y, kC)));
+            }
+            o4[w2] = pack_bf16(ov.x, ov.y);
           }
-          uint4 u;
-          u.x = pack_bf16(o8[0], o8[1]); u.y = pack_bf16(o8[2], o8[3]);
-          u.z = pack_bf16(o8[4], o8[5]); u.w = pack_bf16(o8[6], o8[7]);
-          *reinterpret_cast<uint4*>(s_gy + tile_off(r, 8 * h + 4 * hh + jj)) = u;
+          *reinterpret_cast<uint4*>(s_gy + tile_off(r, (ch0[hh] >> 3) + jj)) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
         }
       }
     }
@@ -427,50 +500,44 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     mark(7);
     if (warp == 0) {
       if (elect_one()) {
-        issue_wgrad(tmem_base + 384, aW[0], aT[2]);  // dW4 += gy^T a2
         issue_gemm(aW[0], aW[2], true);              // D = gy W4
-        mma_commit(bar_m);
+        issue_wgrad(tmem_base + 384, aW[0], aT[2]);  // dW4 += gy^T a2   (under the epilogue of D)
       }
       __syncwarp();
     }
     colsum(s_gy, acc_b[3]);
-    __syncthreads();  // every warp is done reading gy through the generic proxy
-    wait_mma();
-    if (tid == 0) {  // gy is dead: bring W2 back into its slot
+    mark(8);
+    grad_epilogue(s_T[2]);  // g2 -> T2 in place of a2; waits for the weight-gradient MMA before its first store
+    __syncthreads();        // every warp is done reading gy through the generic proxy, and the MMAs reading it are done
+    if (tid == 0) {         // gy is dead: bring W2 back into its slot
       mbar_expect_tx(bar_r, kWBlk);
       bulk_g2s(aW[0], p.wpack, kWBlk, bar_r);
     }
-    mark(8);
-    grad_epilogue(m2, s_T[2]);  // g2 -> T2
     sync_all();
     mark(9);
     if (warp == 0) {
       if (elect_one()) {
-        issue_wgrad(tmem_base + 256, aT[2], aT[1]);  // dW3 += g2^T a1
         issue_gemm(aT[2], aW[1], true);              // D = g2 W3
-        mma_commit(bar_m);
+        issue_wgrad(tmem_base + 256, aT[2], aT[1]);  // dW3 += g2^T a1
       }
       __syncwarp();
     }
     colsum(s_T[2], acc_b[2]);
-    wait_mma();
     mark(10);
-    grad_epilogue(m1, s_T[1]);  // g1 -> T1
+    grad_epilogue(s_T[1]);  // g1 -> T1
     sync_all();
     mark(11);
     if (warp == 0) {
       mbar_wait(bar_r, phase_r);  // W2 is back
       if (elect_one()) {
-        issue_wgrad(tmem_base + 128, aT[1], aT[0]);  // dW2 += g1^T a0
         issue_gemm(aT[1], aW[0], true);              // D = g1 W2
-        mma_commit(bar_m);
+        issue_wgrad(tmem_base + 128, aT[1], aT[0]);  // dW2 += g1^T a0
       }
       __syncwarp();
     }
     wacc = 1;
     phase_r ^= 1;
     colsum(s_T[1], acc_b[1]);
-    wait_mma();
     mark(12);
     // ---- g0 = D . [a0 > 0] (mask re-derived from the a0 tile) -> fp32 staging over T1|T2, 16-byte
     //      chunks XOR-swizzled by row so that both the row-thread writes and the row-cooperative reads
@@ -479,12 +546,13 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     {
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
+        wait_half(hh);
         uint32_t rr_[32];
-        tmem_ld32(d_mine + 32 * hh, rr_);
+        tmem_ld32(d_col[hh], rr_);
         wait_ld();
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
-          const uint4 a8 = *reinterpret_cast<const uint4*>(s_T[0] + tile_off(r, 8 * h + 4 * hh + jj));
+          const uint4 a8 = *reinterpret_cast<const uint4*>(s_T[0] + tile_off(r, (ch0[hh] >> 3) + jj));
           const uint32_t aw[4] = {a8.x, a8.y, a8.z, a8.w};
           float o8[8];
 #pragma unroll
@@ -492,7 +560,11 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
             const uint32_t hw = (aw[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
             o8[e] = hw ? __uint_as_float(rr_[8 * jj + e]) : 0.f;
           }
-          const int c4 = 16 * h + 8 * hh + 2 * jj;  // logical 16-byte chunk of the fp32 row
+          if (hh == 0 && jj == 0) {  // the weight-gradient MMA still reads g1 (T1), which the staging overwrites
+            mbar_wait(bar_g, phase_g);
+            phase_g ^= 1;
+          }
+          const int c4 = (ch0[hh] >> 2) + 2 * jj;  // logical 16-byte chunk of the fp32 row
           *reinterpret_cast<float4*>(s_g0 + r * 128 + (((c4 + 0) ^ (r & 31)) << 2)) = make_float4(o8[0], o8[1], o8[2], o8[3]);
           *reinterpret_cast<float4*>(s_g0 + r * 128 + (((c4 + 1) ^ (r & 31)) << 2)) = make_float4(o8[4], o8[5], o8[6], o8[7]);
         }
@@ -574,7 +646,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
 }
 
 // alignment slack + 3 weight slots + 3 tiles + s_bias[512] + s_F[128] + s_fib[2][128] + s_x[2][128] + s_ij[2][128] + 3 barriers + TMEM address
-size_t edge_chain_bwd_smem() { return 1024 + 6 * kWBlk + 512 * 4 + 128 * 16 * 3 + 256 * 16 + 256 * 8 + 3 * 8 + 16 + 128; }
+size_t edge_chain_bwd_smem() { return 1024 + 6 * kWBlk + 512 * 4 + 128 * 16 * 3 + 256 * 16 + 256 * 8 + 5 * 8 + 16 + 128; }
 
 // Fused bf16 backward of the edge stage.  gPsPd must be zero-filled; gW/gb/gW1 are accumulated into.
 int edge_chain_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const bsms_gmp_grads* gr, const float* PsPd,
@@ -628,7 +700,19 @@ int edge_chain_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, co
     p.prof = d_prof;
   }
   const size_t smem = edge_chain_bwd_smem();
-  auto kern = phase_prof ? k_edge_chain_bwd<true> : k_edge_chain_bwd<false>;
+  // BSMS_BWD_V (development switch): bit 0 = N-split GEMM groups, bit 1 = packed fp32x2 epilogue arithmetic
+  static const int variant = getenv("BSMS_BWD_V") ? atoi(getenv("BSMS_BWD_V")) : 0;
+  void (*kern)(const EdgeBwdParams);
+  switch ((variant & 3) | (phase_prof ? 4 : 0)) {
+    case 0: kern = k_edge_chain_bwd<false, false, false>; break;
+    case 1: kern = k_edge_chain_bwd<false, true, false>; break;
+    case 2: kern = k_edge_chain_bwd<false, false, true>; break;
+    case 3: kern = k_edge_chain_bwd<false, true, true>; break;
+    case 4: kern = k_edge_chain_bwd<true, false, false>; break;
+    case 5: kern = k_edge_chain_bwd<true, true, false>; break;
+    case 6: kern = k_edge_chain_bwd<true, false, true>; break;
+    default: kern = k_edge_chain_bwd<true, true, true>; break;
+  }
   BSMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope ps_(PK_EDGE_CHAIN_BWD, st);
   kern<<<std::min(sms, p.ntiles), 256, smem, st>>>(p);

@@ -4,6 +4,7 @@
 #include <cub/cub.cuh>
 #include <stdarg.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -50,6 +51,31 @@ __global__ void k_plan_keys(const int64_t* __restrict__ g, int64_t E, int64_t N,
   ksrc[e] = (int32_t)s;
   kdst[e] = (int32_t)d;
   iota[e] = (int32_t)e;
+  // status[1] = max sender index: the reference's degree() sizes itself by it (src/utils/basic.py:305-307)
+  const int32_t wmax = __reduce_max_sync(__activemask(), (int32_t)s);
+  if ((threadIdx.x & 31) == 0 || e == 0) atomicMax(&status[1], wmax);
+}
+
+// Content fingerprint of up to 32 buffers of 8-byte words in ONE launch: out[k] = sum_i mix(word_i, i) mod 2^64
+// (splitmix64 finaliser; position-dependent, order of accumulation irrelevant).  blockIdx.y = buffer.
+struct FingerprintArgs {
+  const unsigned long long* ptr[32];
+  long long nwords[32];
+};
+__global__ void k_fingerprint(FingerprintArgs a, unsigned long long* __restrict__ out) {
+  const int k = blockIdx.y;
+  const unsigned long long* p = a.ptr[k];
+  const long long n = a.nwords[k];
+  unsigned long long acc = 0ull;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    unsigned long long z = p[i] + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    acc += z ^ (z >> 31);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out + k, acc);
 }
 
 // gather the other endpoint through the sorted permutation; histogram of the sort key
@@ -101,6 +127,30 @@ extern "C" int bsms_prof_collect(double* ms_by_kind, int64_t* launches_by_kind, 
     cudaEventDestroy(r.b);
   }
   g_prof.clear();
+  return BSMS_OK;
+}
+
+// out_dev[k] (zeroed here) = fingerprint of buffer k; ptrs / nbytes are HOST arrays of n <= 32 entries, sizes
+// multiples of 8.  Asynchronous on `stream`: the host reads out_dev after synchronising.
+extern "C" int bsms_fingerprint(const void* const* ptrs, const int64_t* nbytes, int32_t n, uint64_t* out_dev, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  BSMS_CHECK_ARG(ptrs && nbytes && out_dev && n >= 1 && n <= 32, "bsms_fingerprint: 1..32 buffers");
+  FingerprintArgs a;
+  long long most = 0;
+  for (int k = 0; k < 32; ++k) {
+    a.ptr[k] = nullptr;
+    a.nwords[k] = 0;
+  }
+  for (int k = 0; k < n; ++k) {
+    BSMS_CHECK_ARG(nbytes[k] >= 0 && nbytes[k] % 8 == 0 && (nbytes[k] == 0 || ptrs[k]), "bsms_fingerprint: buffer %d", k);
+    a.ptr[k] = (const unsigned long long*)ptrs[k];
+    a.nwords[k] = nbytes[k] / 8;
+    most = std::max(most, a.nwords[k]);
+  }
+  BSMS_CUDA(cudaMemsetAsync(out_dev, 0, (size_t)n * sizeof(uint64_t), st));
+  const int bx = (int)std::min<long long>(std::max<long long>(ceil_div(most, 256 * 8), 1), 296);
+  k_fingerprint<<<dim3(bx, n), 256, 0, st>>>(a, (unsigned long long*)out_dev);
+  BSMS_LAUNCHED();
   return BSMS_OK;
 }
 

@@ -68,6 +68,13 @@ __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t 
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// TMA 1-D bulk REDUCTION smem -> global: dst[i] += src[i] over `bytes`/4 fp32 values, performed at L2
+// (UBLKRED.G.S.ADD.F32); same visibility / completion rules as bulk_s2g, committed by bulk_commit()
+__device__ __forceinline__ void bulk_red_add_f32(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
@@ -173,6 +180,12 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// relu(lo), relu(hi) -> packed bf16 pair in one conversion (F2FP.RELU.BF16.F32.PACK_AB)
+__device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
 }
 __device__ __forceinline__ uint32_t pack_f16(__half lo, __half hi) {
   __half2 v = __halves2half2(lo, hi);

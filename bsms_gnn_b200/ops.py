@@ -6,6 +6,14 @@ as the reference modules (src/ops/basic.py:6-201, src/ops/BSMS.py:8-104), so
 (src/models/model.py:2) and reference checkpoints load unchanged.  All arithmetic of the processor
 runs in libbsms_b200.so through the C-ABI (include/bsms_b200.h); PyTorch supplies device memory,
 streams and the autograd graph.  There is no CPU path: CPU tensors raise.
+
+Limits compared with the reference modules (they raise `BsmsError` at construction / call time, they never
+fall back): GMP / BSGMP are built for `latent_dim == 128`, `hidden_layer == 3`, `pos_dim` 1..3 (the values of
+every configs/model/*.yaml); tensors must be fp32 CUDA tensors.  Arithmetic modes of the MLP contractions:
+`fp32` (FFMA, exact fp32 products), `fp16x3` (tcgen05, 2-way fp16 split, 3 MMAs, fp32-grade: forward within
+1e-5 of the reference) and `bf16` (tcgen05, one bf16 MMA; activations AND weights are rounded to bf16 at every
+MMA input, the edge-layer biases b2..b4 too because they ride in the MMA; storage and accumulation stay fp32;
+forward within ~5e-3 of the reference).  Standalone `MLP` accepts any shape (it runs the declared torch layers).
 """
 from __future__ import annotations
 
@@ -166,6 +174,10 @@ class GMP(nn.Module):
         return self._run(x, _plan.level_plan(g, x.shape[-2]), pos)
 
 
+_EW_PERM = _plan._Cache(16)   # (ew identity, plan) -> ew in the plan's two edge orders
+_IDS_OK = _plan._Cache(16)    # Unpool index tensors whose range has been checked (identity-keyed)
+
+
 class _ConvFunction(torch.autograd.Function):
     """out = conv(x) in one direction; its adjoint (the other direction) is the backward."""
 
@@ -255,13 +267,20 @@ class WeightedEdgeConv(nn.Module):
         _lib.require_cuda(ew)
         if ew.numel() != level.n_edges:
             raise RuntimeError(f"ew has {ew.numel()} entries for {level.n_edges} edges")
-        ew = ew.detach().to(torch.float32).contiguous()
-        E = max(level.n_edges, 1)
-        ew_d = torch.empty(E, dtype=torch.float32, device=x3.device)
-        ew_s = torch.empty(E, dtype=torch.float32, device=x3.device)
-        with torch.cuda.device(x3.device):
-            check(lib.bsms_permute_ew(level.byref(), ptr(ew), ptr(ew_d), ptr(ew_s), stream_ptr()))
-        out = _ConvFunction.apply(x3, level, ew_d, ew_s, not aggragating)
+        # the weights in the plan's two edge orders are cached per (ew tensor, plan): BSMS.py:74-75,100 call this
+        # three times per level with the same `ew`
+        key = (_plan._ident(ew), id(level))
+        hit = _EW_PERM.get(key)
+        if hit is None:
+            ew32 = ew.detach().to(torch.float32).contiguous()
+            E = max(level.n_edges, 1)
+            ew_d = torch.empty(E, dtype=torch.float32, device=x3.device)
+            ew_s = torch.empty(E, dtype=torch.float32, device=x3.device)
+            with torch.cuda.device(x3.device):
+                check(lib.bsms_permute_ew(level.byref(), ptr(ew32), ptr(ew_d), ptr(ew_s), stream_ptr()))
+            hit = (ew_d, ew_s, ew, level)  # ew / level kept alive: neither identity can be recycled
+            _EW_PERM.put(key, hit)
+        out = _ConvFunction.apply(x3, level, hit[0], hit[1], not aggragating)
         return out if x.dim() == 3 else out.squeeze(0)
 
     @torch.no_grad()
@@ -306,9 +325,17 @@ class Unpool(nn.Module):
             return None  # the reference falls through both branches and returns an unbound name
         h3 = _as_b3(h, "h")
         _lib.require_cuda(idx)
-        if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= pre_node_num):
-            raise IndexError("index out of range in Unpool")
-        out = _UnpoolFunction.apply(h3, idx.to(torch.int32).contiguous(), int(pre_node_num))
+        # range check + int32 copy once per index tensor (one host sync the first time it is seen, none after)
+        key = (_plan._ident(idx), int(pre_node_num))
+        hit = _IDS_OK.get(key)
+        if hit is None:
+            if idx.numel():
+                lo, hi = torch.stack([idx.min(), idx.max()]).tolist()
+                if lo < 0 or hi >= pre_node_num:
+                    raise IndexError("index out of range in Unpool")
+            hit = (idx.to(torch.int32).contiguous(), idx)
+            _IDS_OK.put(key, hit)
+        out = _UnpoolFunction.apply(h3, hit[0], int(pre_node_num))
         return out if h.dim() == 3 else out.squeeze(0)
 
 
@@ -334,6 +361,34 @@ class BSGMP(nn.Module):
                 m.mode = _lib.MODES[mode]
         return self
 
+    def bind_mesh(self, m_gs, m_ids, n0=None):
+        """Pin one hierarchy: later forwards reuse its plan without looking at the index tensors they are
+        handed (only the level sizes are compared).  For callers whose mesh is fixed for the whole run — the
+        reference's consistent-mesh training and its rollout loop (src/utils/rollout_utils.py:48-62) — this
+        removes even the per-step content fingerprint.  `unbind_mesh()` returns to content-keyed look-ups."""
+        d = self.unet_depth
+        _lib.require_cuda(*m_gs[:d + 1], *m_ids[:d])
+        if n0 is None:
+            n0 = int(m_gs[0].max()) + 1 if m_gs[0].numel() else 1
+        self._bound = _plan.hierarchy_plan(list(m_gs[:d + 1]), list(m_ids[:d]), int(n0))
+        return self
+
+    def unbind_mesh(self):
+        self._bound = None
+        return self
+
+    def _hierarchy(self, m_gs, m_ids, n0):
+        d = self.unet_depth
+        hp = getattr(self, "_bound", None)
+        if hp is not None:
+            sizes_ok = (hp.n[0] == n0 and all(int(m_ids[l].shape[0]) == hp.n[l + 1] for l in range(d))
+                        and all(int(m_gs[l].shape[-1]) == hp.levels[l].n_edges for l in range(d + 1)))
+            if not sizes_ok:
+                raise BsmsError("bind_mesh: the hierarchy handed to forward has different level sizes than the bound one; "
+                                "call bind_mesh again or unbind_mesh()")
+            return hp
+        return _plan.hierarchy_plan(list(m_gs[:d + 1]), list(m_ids[:d]), n0)
+
     def forward(self, h, m_ids, m_gs, pos):
         d = self.unet_depth
         if h.dim() not in (2, 3) or pos.dim() not in (2, 3):
@@ -341,7 +396,7 @@ class BSGMP(nn.Module):
         _lib.require_cuda(h, pos, *m_gs[:d + 1], *m_ids[:d])
         if len(m_ids) < d or len(m_gs) < d + 1:
             raise IndexError("list index out of range")  # what the reference's m_gs[i] / m_ids[i] raise
-        hp = _plan.hierarchy_plan(list(m_gs[:d + 1]), list(m_ids[:d]), h.shape[-2])
+        hp = self._hierarchy(m_gs, m_ids, h.shape[-2])
         squeeze = h.dim() == 2
         x = _as_b3(h, "h")
         p = pos.detach().to(torch.float32)

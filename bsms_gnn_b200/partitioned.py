@@ -235,7 +235,7 @@ class PartitionedBSGMP(torch.nn.Module):
         self.states = [RankState(p, device) for p in plans]
         self.ex = exchanger
         self.depth = model.unet_depth
-        self._pos_key, self._pos_cache = None, None
+        self._pos_key, self._pos_cache, self._pos_ref = None, None, None
 
     @staticmethod
     def _gmp(gmp, x_loc, lv, p_loc):
@@ -262,6 +262,9 @@ class PartitionedBSGMP(torch.nn.Module):
         key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in pos_own)
         if key == self._pos_key:
             return self._pos_cache
+        # the key is only meaningful while the tensors it was taken from are alive: keep them, otherwise the
+        # caching allocator can hand the same address (and version 0) to a DIFFERENT position tensor
+        self._pos_ref = list(pos_own)
         d, S, ex = self.depth, self.states, self.ex
         R = range(len(S))
         with torch.no_grad():

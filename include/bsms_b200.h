@@ -72,9 +72,18 @@ typedef struct bsms_level_plan {
 size_t bsms_plan_workspace_bytes(int64_t n_edges, int64_t n_nodes);
 /* Fills the eight arrays of `out` (pre-allocated by the caller with the sizes above) from g.
  * status_dev: int32[4] device scratch; after the call (which synchronises the stream — plan
- * building is one-time, off the hot path) an out-of-range index yields BSMS_EINDEX. */
+ * building is one-time per mesh, off the hot path) an out-of-range index yields BSMS_EINDEX and
+ * status_dev[1] holds max(g[0]) (the reference's degree() sizes itself by it, src/utils/basic.py:305-307). */
 int bsms_plan_build(const int64_t* g, int64_t n_edges, int64_t n_nodes, const bsms_level_plan* out,
                     int32_t* status_dev, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Content fingerprints of n <= 32 device buffers (sizes multiples of 8 bytes) in one launch:
+ * out_dev[k] = position-dependent 64-bit hash of buffer k.  The reference re-uploads m_gs / m_ids
+ * every step (src/trainer/trainer.py:100-117, src/models/model.py:189-200), so the host caches its
+ * plans by CONTENT: one launch + one 8n-byte read-back decides whether a mesh was seen before.
+ * ptrs / nbytes are HOST arrays.  Asynchronous on `stream`. */
+int bsms_fingerprint(const void* const* ptrs_host, const int64_t* nbytes_host, int32_t n,
+                     uint64_t* out_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * WeightedEdgeConv.cal_ew (src/ops/basic.py:142-167): deg_i = out-degree, s_e = w_i/deg_i,

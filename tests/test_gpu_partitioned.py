@@ -57,5 +57,18 @@ def test_partitioned_matches_global(hname, world, mode, ftol, gtol):
         p_own[0].mul_(1.0)  # bumps the version counter
         pm([h[o] for o in own], p_own)
         assert pm._pos_key != key
+        # two DIFFERENT position tensors of the same shape in sequence, the first one dropped in between (the
+        # reference's per-step `node_in[...].clone()`): the allocator may recycle the address, the cache must not
+        # serve the old positions
+        p1 = [pos.to(dev)[o] for o in own]
+        r1 = pm([h[o] for o in own], p1)
+        del p1
+        p2 = [(pos.to(dev) * 1.25)[o] for o in own]
+        r2 = pm([h[o] for o in own], p2)
+        want2 = model(h, [i.to(dev) for i in m_ids], [g.to(dev) for g in m_gs], pos.to(dev) * 1.25)
+        got2 = torch.zeros_like(h)
+        for o, t in zip(own, r2):
+            got2[o] = t
+        assert max_rel(got2, want2) < ftol
     for k, v in model.named_parameters():
         assert max_rel(v.grad, ref_grads[k]) < gtol, k
