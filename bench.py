@@ -379,6 +379,7 @@ def main():
     ap.add_argument("--nx", type=int, default=72)
     ap.add_argument("--depth", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-self-check", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="mesh workload: run the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--workload", default="airfoil", choices=["airfoil", "mesh", "rollout"],
                     help="airfoil: BASELINE.json's metric config (batch-parallel over GPUs); mesh: one large "
@@ -619,6 +620,34 @@ def main():
         else:
             roofline_edge = None
 
+    # ---- untimed self-check (rank 0): the step's own output and input gradient for ONE sample of the batch
+    #      against the CPU oracle (forward) and, in bf16 mode, the fp64 model of the bf16 arithmetic (gradient)
+    self_check = None
+    if rank == 0 and not args.no_self_check:
+        from tests.util import l2_rel, max_rel
+        step(h_dev, pos_dev)
+        torch.cuda.synchronize()
+        gs_c = [torch.from_numpy(g) for g in m_gs]
+        ids_c = [torch.from_numpy(i) for i in m_ids]
+        h1, p1 = h_host[:1].double(), pos_host[:1].double()
+        params64 = {k: v.double() for k, v in O.init_params(args.depth, pos_dim=2, seed=0).items()}
+        with torch.no_grad():
+            out_dev = model(h_dev[:1], ids, gs, pos_dev[:1]).cpu()
+            ref = O.bsgmp(h1, ids_c, gs_c, p1, params64, args.depth)
+        fwd_err = max_rel(out_dev, ref)
+        fwd_tol = 3e-2 if args.mode == "bf16" else 1e-5
+        self_check = {"sample": f"sample 0 of {B}", "forward_max_rel_vs_oracle": fwd_err, "forward_tol": fwd_tol}
+        ok = fwd_err < fwd_tol
+        if args.mode == "bf16":
+            from oracle import bf16_model as M
+            hq = h1.clone().requires_grad_(True)
+            (M.bsgmp_bf16(hq, ids_c, gs_c, p1, params64, args.depth).square().sum() / (B * pos.shape[0] * D)).backward()
+            g_err = l2_rel(h_dev.grad[:1].cpu(), hq.grad)
+            self_check.update(grad_h_l2_rel_vs_bf16_model=g_err, grad_tol=2e-2)
+            ok = ok and g_err < 2e-2
+        self_check["pass"] = bool(ok)
+        assert ok, f"bench self-check failed: {self_check}"
+
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -649,6 +678,7 @@ def main():
                     "ms_per_step": e2e_s * 1e3},
             "gpu_launches": int(launches),
             "roofline": roofline, "roofline_fused_edge_kernel": roofline_edge, "kernel_breakdown": breakdown, "cpu_baseline": cpu,
+            "self_check": self_check,
         }
         print(json.dumps(out))
     if world > 1:

@@ -38,7 +38,7 @@ EXPORTS = [
     "bsms_cal_ew", "bsms_permute_ew", "bsms_edge_conv", "bsms_conv_down_pool", "bsms_unpool_conv_up",
     "bsms_gather_rows", "bsms_unpool_rows", "bsms_gmp_workspace_bytes", "bsms_gmp_saved_bytes", "bsms_gmp_forward",
     "bsms_gmp_backward", "bsms_launch_count", "bsms_prof_enable", "bsms_prof_collect",
-    "bsms_debug_edge_stage",
+    "bsms_debug_edge_stage", "bsms_masked_rmse", "bsms_clip_adamw_step",
 ]
 
 
@@ -75,6 +75,9 @@ def _load():
     lib.bsms_launch_count.restype = i64
     lib.bsms_launch_count.argtypes = []
     lib.bsms_debug_edge_stage.argtypes = [P(LevelPlanC), P(GmpWeightsC), vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, sz, vp]
+    f64 = C.c_double
+    lib.bsms_masked_rmse.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp]
+    lib.bsms_clip_adamw_step.argtypes = [vp, vp, vp, vp, i64, vp, vp, f64, f64, f64, f64, f64, f64, f64, f64, i32, vp]
     lib.bsms_prof_enable.argtypes = [C.c_int]
     lib.bsms_prof_collect.argtypes = [P(C.c_double), P(i64), C.c_int]
     for name in EXPORTS:

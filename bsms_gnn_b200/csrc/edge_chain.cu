@@ -647,6 +647,20 @@ static size_t edge_chain_ws_smem() {
 
 size_t edge_chain_pack_bytes(int mode) { return (size_t)3 * (mode == BSMS_MODE_FP16X3 ? 2 : 1) * kWBlk + 3 * kBiasBlk; }
 
+#define BSMS_TRY_(expr)           \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != BSMS_OK) return _rc; \
+  } while (0)
+
+// b2..b4 -> the shared 16 KB bias operand block of the bf16 kernel
+int edge_chain_pack_bias(const bsms_gmp_weights* w, uint8_t* bpack, cudaStream_t st) {
+  ProfScope ps_(PK_OTHER, st);
+  k_pack_bias3<<<1, 128, 0, st>>>(w->b_edge[1], w->b_edge[2], w->b_edge[3], bpack);
+  BSMS_LAUNCHED();
+  return BSMS_OK;
+}
+
 // Runs the fused edge stage.  aggr must be zero-filled by the caller; PsPd carries b1 in its Pd half.
 // wpack: the packed weight images (scratch when !prepacked); bpack: 16 KB for the shared bias block (bf16).
 int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* PsPd, const float* pos,
@@ -708,11 +722,7 @@ int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, con
       k_pack_weights<1><<<3, 256, 0, st>>>(pk, wpack);
       BSMS_LAUNCHED();
     }
-    {
-      ProfScope ps_(PK_OTHER, st);
-      k_pack_bias3<<<1, 128, 0, st>>>(w->b_edge[1], w->b_edge[2], w->b_edge[3], bpack);
-      BSMS_LAUNCHED();
-    }
+    if (!prepacked) BSMS_TRY_(edge_chain_pack_bias(w, bpack, st));  // prepacked callers packed it with the weights
     const size_t smem = edge_chain_ws_smem();
     auto kern = phase_prof ? k_edge_chain_ws<true> : k_edge_chain_ws<false>;
     BSMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -5,13 +5,13 @@
 // Per 128-edge tile (one tile per CTA at a time, persistent grid, 256 threads = 2 threads per edge
 // row: thread (row r, half h) owns channels [64h, 64h+64) of TMEM lane r):
 //   a0 = relu(Ps[src]+Pd[dst]+b1+F fiber)            row-cooperative gather (one warp per 512 B row) -> T0 (bf16 smem tile)
-//   a1 = relu(a0 W2^T + b2)                           UMMA  D=T0 x W2   -> T1, m1
-//   a2 = relu(a1 W3^T + b3)                           UMMA  D=T1 x W3   -> T2, m2
+//   a1 = relu(a0 W2^T + b2)                           UMMA  D=T0 x W2   -> T1
+//   a2 = relu(a1 W3^T + b3)                           UMMA  D=T1 x W3   -> T2
 //   y  = a2 W4^T + b4 ; gy = LN'(y) * g_aggr[dst]     UMMA  D=T2 x W4   -> the W2 slot (W2 is idle until the last dgrad;
 //                                                     cp.async.bulk brings it back from L2 once gy is consumed)
-//   dW4 += gy^T a2 ; g2 = (gy W4) . m2                UMMA  wgrad(gy,T2), dgrad D=gy x W4(MN)  -> T2
-//   dW3 += g2^T a1 ; g1 = (g2 W3) . m1                UMMA  wgrad(T2,T1), dgrad D=T2 x W3(MN)  -> T1
-//   dW2 += g1^T a0 ; g0 = (g1 W2) . [a0>0]            UMMA  wgrad(T1,T0), dgrad D=T1 x W2(MN)  -> fp32 staging over T1|T2
+//   g2 = (gy W4) . [a2>0] ; dW4 += gy^T a2            UMMA  dgrad D=gy x W4(MN) -> T2 (in place of a2), wgrad(gy,T2) behind it
+//   g1 = (g2 W3) . [a1>0] ; dW3 += g2^T a1            UMMA  dgrad D=T2 x W3(MN) -> T1 (in place of a1), wgrad(T2,T1)
+//   g0 = (g1 W2) . [a0>0] ; dW2 += g1^T a0            UMMA  dgrad D=T1 x W2(MN) -> fp32 staging over T1|T2, wgrad(T1,T0)
 //   gPs[src] += g0 (one coalesced 512 B red.add.v4 per row) ; gPd[dst] += run sums of g0 ; gF += g0^T fiber ; gb* += column sums
 // The three weight-gradient accumulators (3 x 128 TMEM columns) stay resident in tensor memory for
 // the whole persistent loop and are reduced into global memory once per CTA; the activation /
@@ -62,18 +62,34 @@ __device__ __forceinline__ void load_d64(uint32_t taddr, float (&v)[64]) {
   }
 }
 
+// fiber = [pos_i - pos_j, |pos_i - pos_j|] padded to 4 (src/ops/basic.py:83-85), P in {1,2,3} at run time, scalars
+// only: a local array indexed by P would live in local memory and every use would wait for its loads
+__device__ __forceinline__ float4 make_fiber(const float* __restrict__ pb, int P, int i, int j) {
+  const float* a = pb + (size_t)i * P;
+  const float* b = pb + (size_t)j * P;
+  const float d0 = a[0] - b[0];
+  const float d1 = P > 1 ? a[1] - b[1] : 0.f;
+  const float d2 = P > 2 ? a[2] - b[2] : 0.f;
+  const float nrm = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+  return P == 1 ? make_float4(d0, nrm, 0.f, 0.f) : (P == 2 ? make_float4(d0, d1, nrm, 0.f) : make_float4(d0, d1, d2, nrm));
+}
+
 // Structure notes (measured on B200, profiles/r2_bwd_*.txt):
 //  * ReLU + bf16 packing is one cvt (F2FP.RELU), ReLU masks are re-derived from the stored activation tiles
 //    (a > 0 <=> its bf16 image is non-zero), LayerNorm backward is two FMAs per element, and the
 //    weight-gradient MMA of every backward layer is issued AFTER its data-gradient MMA on its own barrier,
 //    so it runs under the epilogue of the data gradient instead of in front of it (8.66 -> 7.88 ms / step).
-//  * NS ("N-split"): every 128x128x128 GEMM is issued as two N = 64 halves with their own barriers, and every
-//    thread owns 32 channels of EACH half, so the epilogue of half 0 runs under the MMA of half 1.
+//  * Measured and rejected: N-split GEMM groups with half-epilogues under the second half's MMA
+//    (8.42 vs 7.91 ms: two N = 64 groups re-read the A operand and take longer than one N = 128 group); the
+//    sender-side scatter as 512-byte bulk reductions (UBLKRED, 8.16 vs 7.88 ms: ~30 cycles of issue each); the
+//    gather of tile i+1 interleaved with the scatter rows of tile i (7.75 vs 7.57 ms: loads and reductions share
+//    the SM's L1/L2 port, the merged phase costs the sum of the two).
 //  * F2: the epilogue arithmetic uses the packed fp32x2 instructions of sm_100 (FADD2 / FFMA2): the epilogues
 //    are bound by the FMA pipe's issue rate, not by latency.
-template <bool PROF, bool NS, bool F2>
+template <bool PROF, bool F2>
 __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
+  constexpr bool NS = false;  // N-split GEMM groups (two N = 64 halves on their own barriers): measured slower, 8.42 vs 7.91 ms
   constexpr uint32_t NH = NS ? 64 : 128;                          // N of one MMA group
   constexpr uint32_t IDESC_KK = make_idesc(1, 128, NH, 0, 0);     // A K-major, B K-major   (recompute)
   constexpr uint32_t IDESC_KM = make_idesc(1, 128, NH, 0, 1);     // A K-major, B MN-major  (dgrad: B = W^T)
@@ -252,23 +268,16 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     int2* s_ij = s_ij2 + (it & 1) * 128;
     if (it == 0 && tid < 128) {
       const long long row_ = (long long)tile * 128 + tid;
-      float fib_[4] = {0.f, 0.f, 0.f, 0.f};
+      float4 fib4 = make_float4(0.f, 0.f, 0.f, 0.f);
       int2 ij = make_int2(-1, -1);
       if (row_ < p.rows) {
         const int b_ = (int)(row_ / p.E);
         const int e_ = (int)(row_ - (long long)b_ * p.E);
         const int i_ = p.src_d[e_], j_ = p.dst_d[e_];
-        const float* pb = p.pos + (p.pos_batched ? (size_t)b_ * p.N * p.P : 0);
-        float nrm = 0.f;
-        for (int k = 0; k < p.P; ++k) {
-          float dlt = pb[(size_t)i_ * p.P + k] - pb[(size_t)j_ * p.P + k];
-          fib_[k] = dlt;
-          nrm += dlt * dlt;
-        }
-        fib_[p.P] = sqrtf(nrm);
+        fib4 = make_fiber(p.pos + (p.pos_batched ? (size_t)b_ * p.N * p.P : 0), p.P, i_, j_);
         ij = make_int2(b_ * p.N + i_, b_ * p.N + j_);
       }
-      s_fib[tid] = make_float4(fib_[0], fib_[1], fib_[2], fib_[3]);
+      s_fib[tid] = fib4;
       s_ij[tid] = ij;
     }
     __syncthreads();
@@ -375,15 +384,10 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       if (elect_one()) issue_gemm(aT[1], aW[1], false);
       __syncwarp();
     }
-    // in the shadow of GEMM 2: position loads of the next tile's end points (stage 2)
-    float npi[3] = {0.f, 0.f, 0.f}, npj[3] = {0.f, 0.f, 0.f};
-    if (nij.x >= 0) {
-      const float* pb = p.pos + (p.pos_batched ? (size_t)nbatch * p.N * p.P : 0);
-      for (int k = 0; k < p.P; ++k) {
-        npi[k] = pb[(size_t)nij.x * p.P + k];
-        npj[k] = pb[(size_t)nij.y * p.P + k];
-      }
-    }
+    // in the shadow of GEMM 2: positions of the next tile's end points -> fiber (stage 2; plain scalars, the loads are
+    // consumed in the shadow of GEMM 3)
+    float4 nfib = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nij.x >= 0) nfib = make_fiber(p.pos + (p.pos_batched ? (size_t)nbatch * p.N * p.P : 0), p.P, nij.x, nij.y);
     mark(4);
     act_epilogue(s_bias + 256, s_T[2]);
     sync_all();
@@ -392,21 +396,9 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       if (elect_one()) issue_gemm(aT[2], aW[2], false);
       __syncwarp();
     }
-    if (tid < 128) {  // in the shadow of GEMM 3: fiber of the next tile's row -> the other metadata buffer (stage 3)
-      float fib_[4] = {0.f, 0.f, 0.f, 0.f};
-      int2 ij = make_int2(-1, -1);
-      if (nij.x >= 0) {
-        float nrm = 0.f;
-        for (int k = 0; k < p.P; ++k) {
-          const float dlt = npi[k] - npj[k];
-          fib_[k] = dlt;
-          nrm += dlt * dlt;
-        }
-        fib_[p.P] = sqrtf(nrm);
-        ij = make_int2(nbatch * p.N + nij.x, nbatch * p.N + nij.y);
-      }
-      s_fib2[((it + 1) & 1) * 128 + tid] = make_float4(fib_[0], fib_[1], fib_[2], fib_[3]);
-      s_ij2[((it + 1) & 1) * 128 + tid] = ij;
+    if (tid < 128) {  // in the shadow of GEMM 3: the next tile's row metadata -> the other buffer (stage 3)
+      s_fib2[((it + 1) & 1) * 128 + tid] = nfib;
+      s_ij2[((it + 1) & 1) * 128 + tid] = nij.x >= 0 ? make_int2(nbatch * p.N + nij.x, nbatch * p.N + nij.y) : make_int2(-1, -1);
     }
     // upstream gradient row g_aggr[dst] (this thread's 2 x 32 channels): issued before the MMA wait
     float2 g[32];
@@ -579,8 +571,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       // red.add per (run, channel) reaches L2; bias / fiber-weight column sums stay in registers
       float4 run = make_float4(0.f, 0.f, 0.f, 0.f);
       int cur = s_ij[warp * 16].y;
-#pragma unroll 4
-      for (int rr = warp * 16; rr < warp * 16 + 16; ++rr) {
+      auto scatter_row = [&](int rr) {
         const float4 gv = *reinterpret_cast<const float4*>(s_g0 + rr * 128 + ((lane ^ (rr & 31)) << 2));
         const int2 ij = s_ij[rr];
         const float4 f = s_fib[rr];
@@ -596,7 +587,9 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
         acc_fl[1].x += gv.x * f.y; acc_fl[1].y += gv.y * f.y; acc_fl[1].z += gv.z * f.y; acc_fl[1].w += gv.w * f.y;
         acc_fl[2].x += gv.x * f.z; acc_fl[2].y += gv.y * f.z; acc_fl[2].z += gv.z * f.z; acc_fl[2].w += gv.w * f.z;
         acc_fl[3].x += gv.x * f.w; acc_fl[3].y += gv.y * f.w; acc_fl[3].z += gv.z * f.w; acc_fl[3].w += gv.w * f.w;
-      }
+      };
+#pragma unroll 4
+      for (int rr = warp * 16; rr < warp * 16 + 16; ++rr) scatter_row(rr);
       if (cur >= 0) red_add_v4(p.gPsPd + (size_t)cur * 256 + 128 + 4 * lane, run.x, run.y, run.z, run.w);
     }
     __syncthreads();  // the staging tiles / row metadata are rewritten by the next tile
@@ -700,19 +693,10 @@ int edge_chain_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, co
     p.prof = d_prof;
   }
   const size_t smem = edge_chain_bwd_smem();
-  // BSMS_BWD_V (development switch): bit 0 = N-split GEMM groups, bit 1 = packed fp32x2 epilogue arithmetic
-  static const int variant = getenv("BSMS_BWD_V") ? atoi(getenv("BSMS_BWD_V")) : 0;
-  void (*kern)(const EdgeBwdParams);
-  switch ((variant & 3) | (phase_prof ? 4 : 0)) {
-    case 0: kern = k_edge_chain_bwd<false, false, false>; break;
-    case 1: kern = k_edge_chain_bwd<false, true, false>; break;
-    case 2: kern = k_edge_chain_bwd<false, false, true>; break;
-    case 3: kern = k_edge_chain_bwd<false, true, true>; break;
-    case 4: kern = k_edge_chain_bwd<true, false, false>; break;
-    case 5: kern = k_edge_chain_bwd<true, true, false>; break;
-    case 6: kern = k_edge_chain_bwd<true, false, true>; break;
-    default: kern = k_edge_chain_bwd<true, true, true>; break;
-  }
+  // BSMS_BWD_F2=0 (development switch) turns the packed fp32x2 epilogue arithmetic off
+  static const bool f2 = !(getenv("BSMS_BWD_F2") && atoi(getenv("BSMS_BWD_F2")) == 0);
+  void (*kern)(const EdgeBwdParams) = f2 ? (phase_prof ? k_edge_chain_bwd<true, true> : k_edge_chain_bwd<false, true>)
+                                         : (phase_prof ? k_edge_chain_bwd<true, false> : k_edge_chain_bwd<false, false>);
   BSMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope ps_(PK_EDGE_CHAIN_BWD, st);
   kern<<<std::min(sms, p.ntiles), 256, smem, st>>>(p);

@@ -272,7 +272,9 @@ int edge_chain_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, co
 // tensor-core orchestration of a whole GMP block (gmp_tc.cu)
 int gmp_forward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos, int pos_batched,
                    const float* skip, float* out, float* saved, int B, int P, int mode, void* ws, size_t ws_bytes,
-                   cudaStream_t st);
+                   cudaStream_t st, const uint8_t* packed);
+size_t gmp_packed_bytes();
+int gmp_pack_tc(const bsms_gmp_weights* w, int P, int mode, uint8_t* packed, cudaStream_t st);
 int gmp_backward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos,
                     int pos_batched, const float* saved, const float* g_out, float* g_x, const bsms_gmp_grads* gr, int B,
                     int P, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -381,9 +383,34 @@ static int check_common(const bsms_level_plan* pl, const bsms_gmp_weights* w, co
   return BSMS_OK;
 }
 
+extern "C" size_t bsms_gmp_packed_bytes(void) { return gmp_packed_bytes(); }
+
+extern "C" int bsms_gmp_pack(const bsms_gmp_weights* w, int32_t P, int32_t mode, void* packed, void* stream) {
+  BSMS_CHECK_ARG(w && packed, "bsms_gmp_pack: null argument");
+  BSMS_CHECK_ARG(P >= 1 && P <= 3, "bsms_gmp_pack: pos_dim %d unsupported (1..3)", P);
+  BSMS_CHECK_ARG(mode == BSMS_MODE_FP16X3 || mode == BSMS_MODE_BF16, "bsms_gmp_pack: only the tensor-core modes pack weights");
+  return gmp_pack_tc(w, P, mode, (uint8_t*)packed, (cudaStream_t)stream);
+}
+
+static int gmp_forward_impl(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos,
+                            int32_t pos_batched, const float* skip, float* out, float* saved, int32_t B, int32_t P,
+                            int32_t mode, void* ws, size_t ws_bytes, void* stream, const void* packed);
+
 extern "C" int bsms_gmp_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos,
                                 int32_t pos_batched, const float* skip, float* out, float* saved, int32_t B, int32_t P,
                                 int32_t mode, void* ws, size_t ws_bytes, void* stream) {
+  return gmp_forward_impl(pl, w, x, pos, pos_batched, skip, out, saved, B, P, mode, ws, ws_bytes, stream, nullptr);
+}
+
+extern "C" int bsms_gmp_forward_packed(const bsms_level_plan* pl, const bsms_gmp_weights* w, const void* packed, const float* x,
+                                       const float* pos, int32_t pos_batched, const float* skip, float* out, float* saved,
+                                       int32_t B, int32_t P, int32_t mode, void* ws, size_t ws_bytes, void* stream) {
+  return gmp_forward_impl(pl, w, x, pos, pos_batched, skip, out, saved, B, P, mode, ws, ws_bytes, stream, packed);
+}
+
+static int gmp_forward_impl(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos,
+                            int32_t pos_batched, const float* skip, float* out, float* saved, int32_t B, int32_t P,
+                            int32_t mode, void* ws, size_t ws_bytes, void* stream, const void* packed) {
   cudaStream_t st = (cudaStream_t)stream;
   BSMS_TRY(check_common(pl, w, x, pos, B, P, mode));
   BSMS_CHECK_ARG(out && ws, "bsms_gmp_forward: null argument");
@@ -392,7 +419,7 @@ extern "C" int bsms_gmp_forward(const bsms_level_plan* pl, const bsms_gmp_weight
     return BSMS_EWORKSPACE;
   }
   if (mode != BSMS_MODE_FP32)
-    return gmp_forward_tc(pl, w, x, pos, pos_batched, skip, out, saved, B, P, mode, ws, ws_bytes, st);
+    return gmp_forward_tc(pl, w, x, pos, pos_batched, skip, out, saved, B, P, mode, ws, ws_bytes, st, (const uint8_t*)packed);
   const long long Rn = (long long)B * pl->n_nodes, Re = (long long)B * pl->n_edges;
   Arena ar(ws, ws_bytes);
   Fp32Acts a = carve(ar, Rn, Re, false, mode == BSMS_MODE_FP32, saved);

@@ -14,6 +14,7 @@ int edge_chain_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, co
                         float* gPsPd, cudaStream_t st, bool prepacked);
 size_t gmp_pack_stride(int mode);
 int gmp_pack_blocks(const PackList& pl, int mode, uint8_t* out, cudaStream_t st);
+int edge_chain_pack_bias(const bsms_gmp_weights* w, uint8_t* bpack, cudaStream_t st);
 int lin_tc(int mode, const float* X0, int ldx0, const float* X1, int ldx1, int KB, int NB, const uint8_t* const* blocks,
            int b_mn, const float* bias, int relu, const float* mask, int ldmask, int accum, float* Y, int ldy,
            long long rows, int kind, cudaStream_t st);
@@ -76,7 +77,9 @@ static int pack_all(const bsms_gmp_weights* w, int P, int mode, uint8_t* wpack, 
   pl.w[BV2] = w->w_node[1]; pl.ld[BV2] = kD;
   pl.w[BV3] = w->w_node[2]; pl.ld[BV3] = kD;
   pl.w[BV4] = w->w_node[3]; pl.ld[BV4] = kD;
-  return gmp_pack_blocks(pl, mode, wpack, st);
+  TC_TRY(gmp_pack_blocks(pl, mode, wpack, st));
+  if (mode == BSMS_MODE_BF16) TC_TRY(edge_chain_pack_bias(w, wpack + kBiasPackOff, st));  // b2..b4 as one MMA operand block
+  return BSMS_OK;
 }
 
 struct NodeBufs {
@@ -161,9 +164,13 @@ static int forward_nodes(const bsms_level_plan* pl, const bsms_gmp_weights* w, c
   return BSMS_OK;
 }
 
+size_t gmp_packed_bytes() { return kScratchBytes; }
+int gmp_pack_tc(const bsms_gmp_weights* w, int P, int mode, uint8_t* packed, cudaStream_t st) { return pack_all(w, P, mode, packed, st); }
+
+// `packed` (may be null): the images made by bsms_gmp_pack for these weights in this mode — nothing is packed here
 int gmp_forward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos, int pos_batched,
                    const float* skip, float* out, float* saved, int B, int P, int mode, void* ws, size_t ws_bytes,
-                   cudaStream_t st) {
+                   cudaStream_t st, const uint8_t* packed) {
   const long long Rn = (long long)B * pl->n_nodes;
   Arena ar(ws, ws_bytes);
   Arena sv(saved, (size_t)-1);
@@ -174,7 +181,12 @@ int gmp_forward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const f
     set_error("bsms_gmp_forward: workspace too small for the tensor-core path");
     return BSMS_EWORKSPACE;
   }
-  TC_TRY(pack_all(w, P, mode, wpack, st));
+  if (packed && !saved)
+    wpack = const_cast<uint8_t*>(packed);
+  else if (packed)
+    BSMS_CUDA(cudaMemcpyAsync(wpack, packed, kScratchBytes, cudaMemcpyDeviceToDevice, st));
+  else
+    TC_TRY(pack_all(w, P, mode, wpack, st));
   return forward_nodes(pl, w, x, pos, pos_batched, B, P, mode, n, wpack, skip, out, st);
 }
 

@@ -180,6 +180,29 @@ int bsms_debug_edge_stage(const bsms_level_plan* plan, const bsms_gmp_weights* w
                           int32_t stage, float* dbg, float* aggr, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The rest of the training step (src/trainer/trainer.py:79-98,134-156).  Device-resident scalars
+ * only: no host synchronisation, CUDA-graph capturable.
+ * ------------------------------------------------------------------------------------------- */
+/* Masked RMSE (trainer.py:96-98): loss = sqrt(sum((pred-tar)^2 * mask) / sum(mask) / C) with
+ * pred, tar [rows, C], mask [rows] (the reference's [B,N,1] mask).  acc2_dev: double[2] scratch.
+ * loss_dev (float[1], may be NULL) receives the loss; grad_pred ([rows, C], may be NULL) receives
+ * d loss / d pred times *g_loss_dev (1 if g_loss_dev is NULL). */
+int bsms_masked_rmse(const float* pred, const float* tar, const float* mask, int64_t rows, int32_t C,
+                     double* acc2_dev, const float* g_loss_dev, float* loss_dev, float* grad_pred,
+                     void* stream);
+/* One optimiser update over flat fp32 buffers of n values (16-byte aligned): global-norm clipping
+ * (torch.nn.utils.clip_grad_norm_, trainer.py:151; max_norm <= 0 disables it) followed by AdamW
+ * (torch.optim.AdamW as configured at trainer.py:24-28) at the learning rate of the reference's
+ * WarmupCosineDecayScheduler (src/utils/basic.py:168-184; warmup_steps = decay_steps = 0 keeps the
+ * rate constant).  state_dev: double[2] = {number of updates done so far, scratch}; zero it once.
+ * hyper_dev: float[4] scratch that receives {lr, 1-beta1^t, sqrt(1-beta2^t), clip coefficient} of
+ * this update (readable afterwards).  zero_grad != 0 clears the gradient buffer in the same pass. */
+int bsms_clip_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                         double* state_dev, float* hyper_dev, double peak_lr, double warmup_steps,
+                         double decay_steps, double beta1, double beta2, double eps,
+                         double weight_decay, double max_norm, int32_t zero_grad, void* stream);
+
 /* Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline pass).
  * Kinds: 0 edge-MLP forward GEMM/chain, 1 node-level forward GEMMs, 2 edge gather+combine,
  * 3 LayerNorm+segment-sum, 4 dgrad, 5 wgrad, 6 LayerNorm backward, 7 edge-gradient segment sums,

@@ -138,3 +138,44 @@ def test_error_conventions(dev):
     bad[0][0, 0] = 999
     with pytest.raises(IndexError):
         model(torch.zeros(144, 128, device=dev), ids, bad, pos.to(dev))
+
+
+def test_bsgmp_bf16_benchmark_configuration_fwd_bwd(dev):
+    """The BENCHMARKED arithmetic (bf16, BASELINE.json config 3) on the benchmark's mesh (72x72 grid, depth 6,
+    batched positions): whole-processor forward AND backward.
+      * forward vs the un-rounded fp64 oracle: 3e-2 max-rel (measured ~5e-3 — bf16 is not the parity mode);
+      * forward, grad_h and ALL 208 parameter gradients vs oracle/bf16_model.py (the oracle's formulas in fp64
+        with bf16 rounding at the kernels' rounding points): L2-relative per tensor.  What is left is the bf16
+        rounding of the gradient tiles inside the backward GEMMs and the reduction order of the red.adds.
+    """
+    from oracle import bf16_model as M
+    from tests.util import l2_rel
+    m_gs, m_ids, pos, d = load_hier("grid72")
+    B = 2
+    gen = torch.Generator().manual_seed(5)
+    h = torch.randn(B, pos.shape[0], 128, generator=gen)
+    ps = pos.unsqueeze(0) + 0.05 * torch.randn(B, pos.shape[0], 2, generator=gen)
+    params = O.init_params(d, pos_dim=2, seed=6)
+    pr = {k: v.double().requires_grad_(True) for k, v in params.items()}
+    hr = h.double().requires_grad_(True)
+    emu = M.bsgmp_bf16(hr, m_ids, m_gs, ps.double(), pr, d)
+    emu.square().mean().backward()
+    with torch.no_grad():
+        ref = O.bsgmp(h.double(), m_ids, m_gs, ps.double(), {k: v.double() for k, v in params.items()}, d)
+    model = build(d, 2, 6, dev, mode="bf16")
+    hg = h.to(dev).requires_grad_(True)
+    out = model(hg, [i.to(dev) for i in m_ids], [g.to(dev) for g in m_gs], ps.to(dev))
+    out.square().mean().backward()
+    torch.cuda.synchronize()
+    e_ref = max_rel(out.detach().cpu(), ref)
+    e_emu = l2_rel(out.detach().cpu(), emu.detach())
+    e_gh = l2_rel(hg.grad.cpu(), hr.grad)
+    errs = {k: l2_rel(v.grad.cpu(), pr[k].grad) for k, v in model.named_parameters()}
+    worst = max(errs, key=errs.get)
+    print(f"\n[bf16 grid72 d6 B{B}] forward vs fp64 oracle max-rel {e_ref:.2e}; vs bf16 model L2 {e_emu:.2e}; grad_h L2 {e_gh:.2e}; "
+          f"{len(errs)} parameter gradients: worst L2 {errs[worst]:.2e} ({worst}), median {sorted(errs.values())[len(errs) // 2]:.2e}")
+    assert len(errs) == 16 * (2 * d + 1)
+    assert e_ref < 3e-2
+    assert e_emu < 5e-3
+    assert e_gh < 2e-2
+    assert errs[worst] < 2e-2, (worst, errs[worst])
