@@ -39,6 +39,8 @@ EXPORTS = [
     "bsms_gather_rows", "bsms_unpool_rows", "bsms_gmp_workspace_bytes", "bsms_gmp_saved_bytes", "bsms_gmp_forward",
     "bsms_gmp_backward", "bsms_launch_count", "bsms_prof_enable", "bsms_prof_collect",
     "bsms_debug_edge_stage", "bsms_masked_rmse", "bsms_clip_adamw_step",
+    "bsms_gmp_packed_bytes", "bsms_gmp_pack", "bsms_gmp_forward_packed",
+    "bsms_encode_in", "bsms_dense128_packed_bytes", "bsms_dense128_pack", "bsms_dense128_stack", "bsms_decode_out",
 ]
 
 
@@ -78,6 +80,16 @@ def _load():
     f64 = C.c_double
     lib.bsms_masked_rmse.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp]
     lib.bsms_clip_adamw_step.argtypes = [vp, vp, vp, vp, i64, vp, vp, f64, f64, f64, f64, f64, f64, f64, f64, i32, vp]
+    lib.bsms_gmp_packed_bytes.restype = sz
+    lib.bsms_gmp_packed_bytes.argtypes = []
+    lib.bsms_gmp_pack.argtypes = [P(GmpWeightsC), i32, i32, vp, vp]
+    lib.bsms_gmp_forward_packed.argtypes = [P(LevelPlanC), P(GmpWeightsC), vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, vp, sz, vp]
+    lib.bsms_encode_in.argtypes = [vp, i64, i32, i32, i32, P(f64), P(f64), vp, vp, vp, vp, vp]
+    lib.bsms_dense128_packed_bytes.restype = sz
+    lib.bsms_dense128_packed_bytes.argtypes = [i32]
+    lib.bsms_dense128_pack.argtypes = [P(vp), i32, i32, vp, vp]
+    lib.bsms_dense128_stack.argtypes = [vp, i64, P(vp), P(vp), i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.bsms_decode_out.argtypes = [vp, i64, i32, i32, vp, vp, P(f64), P(f64), vp, vp, vp, vp, vp, vp]
     lib.bsms_prof_enable.argtypes = [C.c_int]
     lib.bsms_prof_collect.argtypes = [P(C.c_double), P(i64), C.c_int]
     for name in EXPORTS:
@@ -115,6 +127,10 @@ def require_cuda(*tensors):
 def launch_count() -> int:
     return int(lib.bsms_launch_count())
 
+
+# bumped by anything that rewrites parameter storage behind autograd's back (train.FlatAdamW's raw kernel):
+# part of the key of every cache of packed weight images
+WEIGHTS_EPOCH = [0]
 
 _WS = {}
 

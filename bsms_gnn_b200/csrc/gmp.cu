@@ -94,7 +94,7 @@ k_ln_residual(const float* __restrict__ Yn, const float* __restrict__ x, const f
   float4 y = ld4(Yn + r * D + lane * 4);
   float mean, rstd;
   ln_stats(y, mean, rstd);
-  float4 xv = ld4(x + r * D + lane * 4);
+  float4 xv = x ? ld4(x + r * D + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);  // x == nullptr: plain LayerNorm
   float4 o = make_float4((y.x - mean) * rstd + xv.x, (y.y - mean) * rstd + xv.y, (y.z - mean) * rstd + xv.z,
                          (y.w - mean) * rstd + xv.w);
   if (skip) {
@@ -211,6 +211,10 @@ int launch_ln_bwd_rows(const float* Y, const float* g, int ldg, float* gY, long 
   k_ln_bwd<<<ceil_div(rows * 32, 256), 256, 0, st>>>(Y, g, ldg, nullptr, 0, 0, gY, rows);
   BSMS_LAUNCHED();
   return BSMS_OK;
+}
+// Y[rows,128] = (relu)(X[rows,128] W^T + bias) on the exact-fp32 FFMA GEMM (simulator.cu's fp32 mode)
+int fp32_linear128(const float* X, const float* W, const float* bias, int relu, float* Y, long long rows, cudaStream_t st) {
+  return gemm_nt(X, D, nullptr, 0, D, 0, W, D, bias, nullptr, 0, Y, D, rows, D, relu ? GEMM_RELU : 0, st, PK_NODE_FWD_GEMM);
 }
 int launch_add_rows(const float* a, const float* b, int ldb, float* out, long long rows, cudaStream_t st) {
   if (rows == 0) return BSMS_OK;

@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(256, 2) k_lin2(const Lin2Params p) {
             const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
             const float var = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.f / 128.f);
             const float rstd = 1.f / sqrtf(var + 1e-5f);
-            float4 o = ld4(p.res0 + row * 128 + 4 * lane);
+            float4 o = p.res0 ? ld4(p.res0 + row * 128 + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);  // no residual: plain LayerNorm
             o.x += dx * rstd; o.y += dy * rstd; o.z += dz * rstd; o.w += dw * rstd;
             if (p.res1) {
               const float4 s = ld4(p.res1 + row * 128 + 4 * lane);

@@ -89,7 +89,7 @@ class _GMPFunction(torch.autograd.Function):
     the inputs is kept between the two)."""
 
     @staticmethod
-    def forward(ctx, x3, pos, skip3, level, mode, P, *params):
+    def forward(ctx, x3, pos, skip3, level, mode, P, packed, *params):
         B, N, _ = x3.shape
         pos_batched = 1 if pos.dim() == 3 else 0
         params = tuple(p.detach().contiguous() for p in params)
@@ -102,8 +102,8 @@ class _GMPFunction(torch.autograd.Function):
         if mode == _lib.MODE_BF16 and any(ctx.needs_input_grad):
             saved = torch.empty(int(lib.bsms_gmp_saved_bytes(B, N)), dtype=torch.uint8, device=x3.device)
         with torch.cuda.device(x3.device):
-            check(lib.bsms_gmp_forward(level.byref(), C.byref(w), ptr(x3), ptr(pos), pos_batched, ptr(skip3), ptr(out),
-                                       ptr(saved), B, P, mode, ptr(ws), ws.numel(), stream_ptr()))
+            check(lib.bsms_gmp_forward_packed(level.byref(), C.byref(w), ptr(packed), ptr(x3), ptr(pos), pos_batched, ptr(skip3),
+                                              ptr(out), ptr(saved), B, P, mode, ptr(ws), ws.numel(), stream_ptr()))
         ctx.saved_nodes = saved
         ctx.save_for_backward(x3, pos, *params)
         ctx.level, ctx.mode, ctx.P, ctx.has_skip = level, mode, P, skip3 is not None
@@ -127,7 +127,7 @@ class _GMPFunction(torch.autograd.Function):
                                         ptr(ctx.saved_nodes), ptr(g_out), ptr(g_x), C.byref(gw), B, P, mode, ptr(ws),
                                         ws.numel(), stream_ptr()))
         ctx.saved_nodes = None
-        return (g_x, None, g_out if ctx.has_skip else None, None, None, None, *grads)
+        return (g_x, None, g_out if ctx.has_skip else None, None, None, None, None, *grads)
 
 
 class GMP(nn.Module):
@@ -165,8 +165,27 @@ class GMP(nn.Module):
             raise RuntimeError("pos and x disagree on the batch size")
         pos = pos.detach().to(torch.float32).contiguous()
         skip3 = None if skip is None else _as_b3(skip, "skip")
-        out = _GMPFunction.apply(x3, pos, skip3, level, self.mode, self.pos_dim, *self._params())
+        out = _GMPFunction.apply(x3, pos, skip3, level, self.mode, self.pos_dim, self._packed_weights(), *self._params())
         return out if x.dim() == 3 else out.squeeze(0)
+
+    def _packed_weights(self):
+        """Inference only (grad disabled, tensor-core modes): the 16-bit operand images of this block's weights,
+        packed once and reused until a parameter changes (its version counter moves) — the reference's rollout
+        calls the same blocks 599 times per trajectory (src/utils/rollout_utils.py:48-62)."""
+        if torch.is_grad_enabled() or self.mode == _lib.MODE_FP32:
+            return None
+        params = self._params()
+        key = (self.mode, _lib.WEIGHTS_EPOCH[0], tuple((p.data_ptr(), p._version) for p in params))
+        hit = getattr(self, "_pack_cache", None)
+        if hit is None or hit[0] != key:
+            dev = params[0].device
+            packed = torch.empty(int(lib.bsms_gmp_packed_bytes()), dtype=torch.uint8, device=dev)
+            w = _weights_struct([p.detach().contiguous() for p in params])
+            with torch.cuda.device(dev):
+                check(lib.bsms_gmp_pack(C.byref(w), self.pos_dim, self.mode, ptr(packed), stream_ptr()))
+            hit = (key, packed)
+            self._pack_cache = hit
+        return hit[1]
 
     def forward(self, x, g, pos):
         if x.dim() not in (2, 3):

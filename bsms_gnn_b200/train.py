@@ -105,6 +105,7 @@ class FlatAdamW:
         with torch.cuda.device(self.flat_p.device):
             check(lib.bsms_clip_adamw_step(ptr(self.flat_p), ptr(self.flat_g), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.n,
                                            ptr(self.state), ptr(self.hyper), lr, wu, dc, b1, b2, eps, wd, mn, 0, stream_ptr()))
+        _lib.WEIGHTS_EPOCH[0] += 1  # packed weight images cached for inference are stale now
         self.zero_grad()
 
     # read-backs (synchronise): for logging / tests only

@@ -159,6 +159,16 @@ int bsms_gmp_forward(const bsms_level_plan* plan, const bsms_gmp_weights* w, con
                      const float* pos, int32_t pos_batched, const float* skip /* may be NULL */,
                      float* out, float* saved /* may be NULL */, int32_t B, int32_t P, int32_t mode,
                      void* workspace, size_t workspace_bytes, void* stream);
+/* Inference / rollout form: the 16-bit operand images of a GMP's weights can be made ONCE
+ * (bsms_gmp_pack into bsms_gmp_packed_bytes() bytes, tensor-core modes only) and handed to every
+ * forward while the weights do not change — the reference's rollout (src/utils/rollout_utils.py:48-62)
+ * calls the same 13 blocks 599 times.  `packed` may be NULL (then it is bsms_gmp_forward). */
+size_t bsms_gmp_packed_bytes(void);
+int bsms_gmp_pack(const bsms_gmp_weights* w, int32_t P, int32_t mode, void* packed, void* stream);
+int bsms_gmp_forward_packed(const bsms_level_plan* plan, const bsms_gmp_weights* w, const void* packed,
+                            const float* x, const float* pos, int32_t pos_batched, const float* skip,
+                            float* out, float* saved, int32_t B, int32_t P, int32_t mode,
+                            void* workspace, size_t workspace_bytes, void* stream);
 /* Backward of the block above by recomputation (nothing is saved by forward): given g_out
  * [B,N,128] writes g_x [B,N,128] (gradient w.r.t. x INCLUDING the residual path; the gradient
  * w.r.t. skip is g_out itself) and accumulates the 16 parameter gradients.  No gradient flows to
@@ -202,6 +212,34 @@ int bsms_clip_adamw_step(float* params, float* grads, float* exp_avg, float* exp
                          double* state_dev, float* hyper_dev, double peak_lr, double warmup_steps,
                          double decay_steps, double beta1, double beta2, double eps,
                          double weight_decay, double max_norm, int32_t zero_grad, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The caller side of the processor for inference / rollouts, fused around it
+ * (src/models/model.py:83-106,127-164; src/utils/normalizer.py:39-52,80-83;
+ * src/utils/rollout_utils.py:48-62).  node_in rows are [state(C) | mesh_pos(P) | node_type(1)],
+ * Cin = C + P + 1, C = out_dim <= 4.  mean / std are HOST arrays of doubles (the reference's
+ * normalisers are fp64: mean() and std_with_epsilon()).
+ * ------------------------------------------------------------------------------------------- */
+/* a1 = relu(W0 * normalise([state, type]) + b0) [rows,128] (first encoder layer, model.py:137-147,
+ * W0 = encode.seq.0.weight [128, C+1]) and pos [rows,P] (model.py:62). */
+int bsms_encode_in(const float* node_in, int64_t rows, int32_t Cin, int32_t C, int32_t P,
+                   const double* mean_host, const double* std_host, const float* W0, const float* b0,
+                   float* a1, float* pos, void* stream);
+/* n_layers (1..3) Linear 128->128 layers with ReLU where bit l of relu_mask is set, optionally
+ * followed by LayerNorm without affine (src/ops/basic.py:6-23), in arithmetic `mode`.  W / b are
+ * HOST arrays of device pointers; `packed` from bsms_dense128_pack (unused in BSMS_MODE_FP32);
+ * scratch: 2 * rows * 128 floats. */
+size_t bsms_dense128_packed_bytes(int32_t mode);
+int bsms_dense128_pack(const float* const* W_host, int32_t n_layers, int32_t mode, void* packed, void* stream);
+int bsms_dense128_stack(const float* x, int64_t rows, const float* const* W_host, const float* const* b_host,
+                        int32_t n_layers, int32_t relu_mask, int32_t layer_norm, int32_t mode,
+                        const void* packed, float* out, float* scratch, void* stream);
+/* pred = state + mask * denormalise(W3 y + b3)  (last decoder layer decode.seq.6 [C,128],
+ * model.py:150-163) and, when next_in != NULL, the next rollout input
+ * next_in = mask == 0 ? ic : [pred | pos | type]  (rollout_utils.py:57-62; ic may be NULL). */
+int bsms_decode_out(const float* y, int64_t rows, int32_t Cin, int32_t C, const float* W3, const float* b3,
+                    const double* mean_host, const double* std_host, const float* node_in,
+                    const float* mask, const float* ic, float* pred, float* next_in, void* stream);
 
 /* Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline pass).
  * Kinds: 0 edge-MLP forward GEMM/chain, 1 node-level forward GEMMs, 2 edge gather+combine,
