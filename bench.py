@@ -165,9 +165,11 @@ def host_ram_gb():
         return 0.0
 
 
-def run_mesh(args):
-    """BASELINE.json config 5: one large synthetic mesh, B=1, fwd+bwd, node-partitioned over the ranks
-    with halo exchanges (strong scaling: the mesh is fixed, N GPUs split it)."""
+def measure_mesh(args, rank, world, local_rank, dev, nx, depth, steps, warmup, want_single=False):
+    """One large synthetic mesh, B=1, fwd+bwd, node-partitioned over the ranks (strong scaling).  Returns a dict
+    (rank 0: filled; other ranks: timing fields only).  The process group must already be initialised for world > 1.
+    want_single: rank 0 additionally times the SAME mesh un-partitioned on its own GPU (the N = 1 reference of the
+    strong-scaling ratio) while the other ranks wait."""
     import torch.distributed as dist
     from bsms_gnn_b200 import _lib, hierarchy, meshgen, partition
     from bsms_gnn_b200.dist import GradBucket
@@ -175,15 +177,6 @@ def run_mesh(args):
     from bsms_gnn_b200.partitioned import DistExchanger, PartitionedBSGMP, exchange_requests
     from oracle import bsms_oracle as O
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    nx = args.nx if args.nx != 72 else 1414
-    depth = args.depth
     cache = f"/tmp/bsms_mesh_{nx}_{depth}.npz"
     t0 = time.perf_counter()
     if rank == 0 and not os.path.exists(cache):
@@ -205,9 +198,16 @@ def run_mesh(args):
     params = list(model.parameters())
     gen = torch.Generator().manual_seed(7)
     h_all = torch.randn(n0, D, generator=gen)
+    exchange = "none"
     if world > 1:
         plan = exchange_requests(partition.build_rank_plan(m_gs, m_ids, n0, world, rank))
-        pm = PartitionedBSGMP(model, [plan], DistExchanger(), dev)
+        if args.exchange == "push":
+            from bsms_gnn_b200.halo import PushExchanger
+            pm = PartitionedBSGMP(model, [plan], PushExchanger(), dev, pos_exchanger=DistExchanger())
+            exchange = "one push kernel per exchange over CUDA-IPC peer memory (bsms_halo_exchange)"
+        else:
+            pm = PartitionedBSGMP(model, [plan], DistExchanger(), dev)
+            exchange = "index_select + NCCL point-to-point group + index_add_"
         own = torch.from_numpy(plan.levels[0].nodes[:plan.levels[0].n_own])
         h_host = h_all[own].contiguous().pin_memory()
         p_dev = torch.from_numpy(pos)[own].to(dev)
@@ -216,9 +216,11 @@ def run_mesh(args):
     else:
         h_host = h_all.pin_memory()
         p_dev = torch.from_numpy(pos).to(dev)
+        ghosts = None
+    gs = ids = None
+    if world == 1 or (want_single and rank == 0):
         gs = [torch.from_numpy(g).to(dev) for g in m_gs]
         ids = [torch.from_numpy(i).to(dev) for i in m_ids]
-        ghosts = None
     setup_s = time.perf_counter() - t0
     h_dev = h_host.to(dev).requires_grad_(True)
 
@@ -242,43 +244,92 @@ def run_mesh(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    def timed(run, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            run()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / n
+
+    for _ in range(warmup):
         step(h_dev)
     barrier()
     n0l = _lib.launch_count()
     step(h_dev)
     launches_per_step = _lib.launch_count() - n0l
     run = lambda: step(h_dev)
+    graph = None
     if not args.no_graph:
         # the whole step (forward, backward, halo exchanges, gradient all-reduce) replayed from ONE CUDA graph
         from bsms_gnn_b200.graphed import GraphedStep
-        run = GraphedStep(lambda: step(h_dev), warmup=1)
+        graph = GraphedStep(lambda: step(h_dev), warmup=1)
+        run = graph
         for _ in range(2):
             run()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as cs:
-        e0.record()
-        for _ in range(args.steps):
-            run()
-        e1.record()
-        barrier()
-    launches = launches_per_step * args.steps
-    ms = e0.elapsed_time(e1) / args.steps
+        ms = timed(run, steps)
     # end to end: this step's features come from pinned host memory, the loss goes back to the host
+    barrier()
     t1 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         with torch.no_grad():
             h_dev.copy_(h_host, non_blocking=True)
         _ = run().item()
     torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t1) / args.steps
+    e2e_s = (time.perf_counter() - t1) / steps
     if world > 1:
         t = torch.tensor([ms, e2e_s * 1e3], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1]) / 1e3
+    res = {"ms_per_step": ms, "e2e_ms_per_step": e2e_s * 1e3, "launches_per_step": int(launches_per_step), "ghosts": ghosts,
+           "setup_s": setup_s, "n0": n0, "E0": E0, "edge_rows": edge_rows, "clocks": cs.result, "exchange": exchange,
+           "h2d_bytes_per_step": int(h_host.numel() * 4), "graph": graph, "single_ms_per_step": None}
+    if want_single and world > 1:
+        # the N = 1 reference of the strong-scaling ratio: the same mesh, un-partitioned, on rank 0's GPU
+        if rank == 0:
+            h1 = h_all.to(dev).requires_grad_(True)
+            p1 = torch.from_numpy(pos).to(dev)
+
+            def step1():
+                for q in params:
+                    q.grad = None
+                h1.grad = None
+                model(h1, ids, gs, p1).square().mean().backward()
+
+            for _ in range(2):
+                step1()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(max(3, steps // 2)):
+                step1()
+            e1.record()
+            torch.cuda.synchronize()
+            res["single_ms_per_step"] = e0.elapsed_time(e1) / max(3, steps // 2)
+            del h1, p1
+        dist.barrier()
+    return res
+
+
+def run_mesh(args):
+    """BASELINE.json config 5: one large synthetic mesh, B=1, fwd+bwd, node-partitioned over the ranks
+    with halo exchanges (strong scaling: the mesh is fixed, N GPUs split it)."""
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nx = args.nx if args.nx != 72 else 1414
+    depth = args.depth
+    r = measure_mesh(args, rank, world, local_rank, dev, nx, depth, args.steps, args.warmup, want_single=args.single_ref)
     if rank == 0:
-        clk = cs.result
+        clk, ms, n0, E0 = r["clocks"], r["ms_per_step"], r["n0"], r["E0"]
         print(json.dumps({
             "metric": "M-edges/s per BSMS fwd+bwd step", "value": E0 / (ms * 1e-3) / 1e6, "unit": "M-edges/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -287,83 +338,149 @@ def run_mesh(args):
             "data": "synthetic",
             "config": {"workload": f"synthetic {nx}x{nx} tri-grid ({n0} nodes / {E0} directed edges), unet_depth {depth}, "
                                    f"latent 128, B=1, fwd+bwd", "mode": args.mode,
-                       "parallelism": (f"node partition x{world}, {4 * depth + 1} halo exchanges per forward (NCCL p2p), "
+                       "parallelism": (f"node partition x{world}, {4 * depth + 1} halo exchanges per forward ({r['exchange']}), "
                                        f"grad all-reduce") if world > 1 else "single GPU",
                        "execution": "eager" if args.no_graph else "whole step replayed from one CUDA graph",
-                       "rank0_ghost_rows_per_level": ghosts, "setup_s": setup_s,
+                       "rank0_ghost_rows_per_level": r["ghosts"], "setup_s": r["setup_s"],
                        "l2": "per-step working set far exceeds the 126 MB L2"},
-            "edge_evals_per_s": edge_rows / (ms * 1e-3),
+            "edge_evals_per_s": r["edge_rows"] / (ms * 1e-3),
+            "single_gpu_ms_per_step_same_run": r["single_ms_per_step"],
+            "speedup_vs_single_gpu_same_run": (r["single_ms_per_step"] / ms) if r["single_ms_per_step"] else None,
             "clocks": {"sm_mhz": clk.get("sm_mhz"), "sm_max_mhz": clk.get("sm_max_mhz"), "reasons": clk.get("reasons")},
-            "e2e": {"value": E0 / e2e_s / 1e6, "unit": "M-edges/s", "h2d_bytes_per_step": int(h_host.numel() * 4),
-                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3},
-            "gpu_launches": int(launches)}), flush=True)
+            "e2e": {"value": E0 / (r["e2e_ms_per_step"] * 1e-3) / 1e6, "unit": "M-edges/s", "h2d_bytes_per_step": r["h2d_bytes_per_step"],
+                    "d2h_bytes_per_step": 4, "ms_per_step": r["e2e_ms_per_step"]},
+            "gpu_launches": int(r["launches_per_step"] * args.steps)}), flush=True)
     if world > 1:
-        if not args.no_graph:
-            # a process group whose NCCL work was captured into a live CUDA graph does not tear down cleanly:
-            # drop the graph, drain the device and leave without the collective destructor
-            del run
-            torch.cuda.synchronize()
-            dist.barrier()
-            torch.cuda.synchronize()
-            sys.stdout.flush()
-            os._exit(0)
-        dist.destroy_process_group()
+        leave_group(r["graph"] is not None)
+
+
+def leave_group(graph_captured_nccl):
+    import torch.distributed as dist
+    if graph_captured_nccl:
+        # a process group whose NCCL work was captured into a live CUDA graph does not tear down cleanly:
+        # drain the device and leave without the collective destructor
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
+    dist.destroy_process_group()
+
+
+class _SimModel(torch.nn.Module):
+    """The attributes of the reference's BSMS_Simulator (src/models/model.py:20-27) that the fused rollout reads:
+    encoder / processor / decoder built from this package's ops, and fixed normaliser statistics."""
+
+    class _Norm:
+        def __init__(self, mean, std):
+            self._m, self._s = mean, std
+
+        def mean(self):
+            return self._m
+
+        def std_with_epsilon(self):
+            return self._s
+
+    def __init__(self, depth, C, P, mode, dev, seed=0):
+        super().__init__()
+        from bsms_gnn_b200.ops import BSGMP, MLP
+        from oracle import bsms_oracle as O
+        torch.manual_seed(seed)
+        self.encode = MLP(C + 1, D, D, 3, True)
+        self.process = BSGMP(depth, D, 3, P, mode=mode)
+        self.decode = MLP(D, D, C, 3, False)
+        self.process.load_state_dict(O.init_params(depth, pos_dim=P, seed=seed))
+        self.pos_dim = P
+        self.to(dev)
+        self._inputNormalizer = self._Norm(torch.zeros(C + 1, dtype=torch.float64), torch.ones(C + 1, dtype=torch.float64))
+        # small target std: the random-init network then perturbs the state by ~1e-2 per step, like a trained one
+        self._targetNormalizer = self._Norm(torch.zeros(C, dtype=torch.float64), torch.full((C,), 1e-2, dtype=torch.float64))
 
 
 def run_rollout(args):
-    """BASELINE.json config 2 (CylinderFlow-like 44x44, unet_depth 5, B=1): T sequential processor
-    forwards with feedback, the reference's rollout pattern (src/utils/rollout_utils.py:48-62).
-    Reports ms per forward eagerly and replayed from a CUDA graph."""
-    from bsms_gnn_b200 import _lib
-    from bsms_gnn_b200.graphed import GraphedBSGMP
-    from bsms_gnn_b200.ops import BSGMP
-    from oracle import bsms_oracle as O
+    """BASELINE.json configs 2 and 4: T sequential whole-model forwards with feedback, B = 1 — the reference's
+    rollout_one_traj (src/utils/rollout_utils.py:15-64): encoder -> processor -> decoder, normalisers, mask,
+    residual, next input = prediction with the boundary nodes re-imposed.
+      --mesh cylinder (config 2): 44x44 tri-grid, unet_depth 5, out_dim 2, static mesh positions;
+      --mesh sphere   (config 4): icosphere-5 (10 242 nodes / 61 440 directed edges), pos_dim = out_dim = 3, unet_depth 6,
+                                  the mesh positions the processor sees change EVERY step (= the predicted state).
+    Device time per step from CUDA events over T graph replays; e2e adds a pinned-host copy of every step's state."""
+    from bsms_gnn_b200 import _lib, hierarchy, meshgen
+    from bsms_gnn_b200.simulator import FusedSimulator, GraphedRollout
 
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
-    nx = args.nx if args.nx != 72 else 44
-    depth = args.depth if args.nx != 72 else 5
-    pos, m_gs, m_ids = build_workload(nx, depth)
-    E0 = int(m_gs[0].shape[1])
+    if args.mesh == "sphere":
+        pos, cells = meshgen.icosphere(5)
+        depth, C, P, name = 6, 3, 3, "icosphere-5"
+        m_gs, m_ids = hierarchy.build_hierarchy(meshgen.cells_to_flat_edge(cells), depth, pos.shape[0], pos)
+    else:
+        nx = args.nx if args.nx != 72 else 44
+        depth = args.depth if args.nx != 72 else 5
+        pos, m_gs, m_ids = build_workload(nx, depth)
+        C, P, name = 2, 2, f"cylinder-like {nx}x{nx} tri-grid"
+    N, E0 = pos.shape[0], int(m_gs[0].shape[1])
     edge_rows = 2 * sum(int(g.shape[1]) for g in m_gs[:depth]) + int(m_gs[depth].shape[1])
     mode = args.mode
-    model = BSGMP(depth, D, 3, 2, mode=mode).to(dev)
-    model.load_state_dict(O.init_params(depth, pos_dim=2, seed=0))
+    model = _SimModel(depth, C, P, mode, dev)
+    sim = FusedSimulator(model, mode=mode, pos_feedback=(args.mesh == "sphere"))
     gs = [torch.from_numpy(g).to(dev) for g in m_gs]
     ids = [torch.from_numpy(i).to(dev) for i in m_ids]
-    p = torch.from_numpy(pos).to(dev)
-    h0 = torch.randn(pos.shape[0], D, generator=torch.Generator().manual_seed(3)).to(dev)
-    T = max(args.steps, 10) if args.steps != 10 else 599
-    graphed = GraphedBSGMP(model, ids, gs, h0, p)
-
-    def timed(fn):
-        x = h0
+    gen = torch.Generator().manual_seed(3)
+    ntype = (torch.rand(1, N, 1, generator=gen) > 0.9).float()
+    p0 = torch.from_numpy(pos).unsqueeze(0)
+    state0 = p0.clone() if args.mesh == "sphere" else torch.randn(1, N, C, generator=gen)
+    ic = torch.cat([state0, p0, ntype], -1).to(dev)
+    mask = (ntype == 0).float().to(dev)
+    T = args.steps if args.steps != 10 else 599
+    with torch.no_grad():
+        # eager (no graph): python + launch bound
         for _ in range(args.warmup):
-            x = fn(x)
+            sim.rollout(ic, mask, gs, ids, 3)
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        x = h0
-        for _ in range(T):
-            x = fn(x)
+        res_eager = sim.rollout(ic, mask, gs, ids, min(T, 100))
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / T, _lib.launch_count() - n0
-
-    with torch.no_grad():
-        ms_eager, launches = timed(lambda x: model(x, ids, gs, p))
-        ms_graph, _ = timed(lambda x: graphed(x))
+        ms_eager = e0.elapsed_time(e1) / min(T, 100)
+        launches = (_lib.launch_count() - n0) / min(T, 100)
+        gr = GraphedRollout(sim, ic, mask, gs, ids)
+        for _ in range(args.warmup):
+            gr.step()
+        gr.reset()
+        torch.cuda.synchronize()
+        with ClockSampler(0) as cs:
+            e0.record()
+            res = gr.run(T)
+            e1.record()
+            torch.cuda.synchronize()
+        ms_graph = e0.elapsed_time(e1) / T
+        assert torch.isfinite(res).all()
+        err = float((res[:min(T, 100)] - res_eager).abs().max() / res_eager.abs().max())
+        # e2e: every step's state goes back to pinned host memory
+        host = torch.empty(T, N, C, dtype=torch.float32).pin_memory()
+        gr.reset()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        gr.run(T, host=host)
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / T
+    clk = cs.result
     print(json.dumps({
-        "metric": "M-edges/s per BSMS forward (rollout)", "value": E0 / (ms_graph * 1e-3) / 1e6, "unit": "M-edges/s",
+        "metric": "M-edges/s per BSMS forward (rollout step, whole model)", "value": E0 / (ms_graph * 1e-3) / 1e6, "unit": "M-edges/s",
         "n_gpus": 1, "steps": T, "warmup": args.warmup, "ms_per_step": ms_graph, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": mode, "data": "synthetic",
-        "config": {"workload": f"cylinder-like {nx}x{nx} tri-grid ({pos.shape[0]} nodes / {E0} directed edges), "
-                               f"unet_depth {depth}, B=1, forward rollout of {T} sequential steps with feedback",
-                   "mode": mode, "execution": "CUDA graph replay"},
-        "ms_per_forward_eager": ms_eager, "ms_per_forward_graph": ms_graph,
-        "edge_evals_per_s": edge_rows / (ms_graph * 1e-3), "gpu_launches": int(launches),
-        "kernels_per_forward": launches / T}))
+        "config": {"workload": f"{name} ({N} nodes / {E0} directed edges), unet_depth {depth}, out_dim {C}, pos_dim {P}, B=1, "
+                               f"rollout of {T} sequential whole-model steps with on-device feedback and boundary re-imposition"
+                               + (", mesh positions updated every step" if args.mesh == "sphere" else ""),
+                   "mode": mode, "execution": "one CUDA graph per step (encoder + processor + decoder + feedback)"},
+        "ms_per_step_eager": ms_eager, "ms_per_step_graph": ms_graph, "graph_vs_eager_max_rel": err,
+        "edge_evals_per_s": edge_rows / (ms_graph * 1e-3), "gpu_launches": int(launches * T), "kernels_per_step": launches,
+        "clocks": {"sm_mhz": clk.get("sm_mhz"), "sm_max_mhz": clk.get("sm_max_mhz"), "reasons": clk.get("reasons")},
+        "e2e": {"value": E0 / (e2e_ms * 1e-3) / 1e6, "unit": "M-edges/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": int(N * C * 4), "note": "the input of step k+1 is produced on the device by step k; every state is copied to pinned host memory"}}))
 
 
 def main():
@@ -380,6 +497,10 @@ def main():
     ap.add_argument("--depth", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-self-check", action="store_true")
+    ap.add_argument("--mesh-nx", type=int, default=1414, help="N > 1: side of the strong-scaling mesh reported in extra.mesh_strong")
+    ap.add_argument("--exchange", default="push", choices=["push", "nccl"], help="mesh workload, N > 1: halo exchange implementation")
+    ap.add_argument("--single-ref", action="store_true", help="mesh workload, N > 1: rank 0 also times the un-partitioned mesh")
+    ap.add_argument("--mesh", default="cylinder", choices=["cylinder", "sphere"], help="rollout workload: config 2 / config 4")
     ap.add_argument("--no-graph", action="store_true", help="mesh workload: run the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--workload", default="airfoil", choices=["airfoil", "mesh", "rollout"],
                     help="airfoil: BASELINE.json's metric config (batch-parallel over GPUs); mesh: one large "
@@ -658,6 +779,29 @@ def main():
                "sample": f"batch {b_cpu} of {B} (same mesh and weights), {len(times)} fwd+bwd steps after {w_done} warm-up, "
                          f"{t * 1e3:.0f} ms each; the full batch is timed by --impl reference"}
 
+    # ---- N > 1: BASELINE.json config 5 in the same run — the 2.0 M-node / 12.0 M-edge mesh node-partitioned over the
+    #      N GPUs (strong scaling), with the un-partitioned step timed on rank 0 as the N = 1 reference
+    mesh_strong, mesh_graph = None, False
+    if world > 1 and os.environ.get("BSMS_BENCH_MESH", "1") != "0":
+        del bufs
+        torch.cuda.empty_cache()
+        mr = measure_mesh(args, rank, world, local_rank, dev, args.mesh_nx, 6, max(5, min(args.steps, 10)), 3, want_single=True)
+        mesh_graph = mr["graph"] is not None
+        if rank == 0:
+            mesh_strong = {"workload": f"synthetic {args.mesh_nx}x{args.mesh_nx} tri-grid ({mr['n0']} nodes / {mr['E0']} directed edges), "
+                                       f"unet_depth 6, B=1, fwd+bwd, {args.mode}", "n_gpus": world, "ms_per_step": mr["ms_per_step"],
+                           "value": mr["E0"] / (mr["ms_per_step"] * 1e-3) / 1e6, "unit": "M-edges/s",
+                           "single_gpu_ms_per_step": mr["single_ms_per_step"],
+                           "speedup_vs_n1": (mr["single_ms_per_step"] / mr["ms_per_step"]) if mr["single_ms_per_step"] else None,
+                           "e2e": {"ms_per_step": mr["e2e_ms_per_step"], "h2d_bytes_per_step": mr["h2d_bytes_per_step"],
+                                   "d2h_bytes_per_step": 4,
+                                   "speedup_vs_n1_device_time": (mr["single_ms_per_step"] / mr["e2e_ms_per_step"]) if mr["single_ms_per_step"] else None},
+                           "halo_exchange": mr["exchange"], "exchanges_per_step": 2 * (4 * 6 + 1),
+                           "execution": "eager" if args.no_graph else "whole step replayed from one CUDA graph",
+                           "rank0_ghost_rows_per_level": mr["ghosts"], "setup_s": mr["setup_s"],
+                           "gpu_launches_per_step": mr["launches_per_step"],
+                           "n1_reference": "the same mesh un-partitioned on rank 0's GPU, eager, CUDA events, same run"}
+
     if rank == 0:
         value = world * B * E0 / (ms * 1e-3) / 1e6
         clk = cs.result
@@ -678,11 +822,11 @@ def main():
                     "ms_per_step": e2e_s * 1e3},
             "gpu_launches": int(launches),
             "roofline": roofline, "roofline_fused_edge_kernel": roofline_edge, "kernel_breakdown": breakdown, "cpu_baseline": cpu,
-            "self_check": self_check,
+            "self_check": self_check, "extra": {"mesh_strong": mesh_strong},
         }
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        leave_group(mesh_graph)
 
 
 if __name__ == "__main__":

@@ -33,6 +33,14 @@ class GmpWeightsC(C.Structure):
                 ("w_node", C.c_void_p * 4), ("b_node", C.c_void_p * 4)]
 
 
+class HaloArgsC(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("channels", C.c_int32), ("backward", C.c_int32),
+                ("n_own", C.c_int64), ("n_ghost", C.c_int64), ("n_send", C.c_int64),
+                ("src", C.c_void_p), ("dst", C.c_void_p), ("send_idx", C.c_void_p),
+                ("send_off", C.c_int32 * 9), ("recv_off", C.c_int32 * 9), ("peer_dst", C.c_void_p * 8),
+                ("back", C.c_void_p), ("my_flags", C.c_void_p), ("peer_flag", C.c_void_p * 8), ("ctrl", C.c_void_p)]
+
+
 EXPORTS = [
     "bsms_last_error", "bsms_version", "bsms_device_info", "bsms_plan_workspace_bytes", "bsms_plan_build", "bsms_fingerprint",
     "bsms_cal_ew", "bsms_permute_ew", "bsms_edge_conv", "bsms_conv_down_pool", "bsms_unpool_conv_up",
@@ -40,6 +48,7 @@ EXPORTS = [
     "bsms_gmp_backward", "bsms_launch_count", "bsms_prof_enable", "bsms_prof_collect",
     "bsms_debug_edge_stage", "bsms_masked_rmse", "bsms_clip_adamw_step",
     "bsms_gmp_packed_bytes", "bsms_gmp_pack", "bsms_gmp_forward_packed",
+    "bsms_ipc_alloc", "bsms_ipc_free", "bsms_ipc_export", "bsms_ipc_open", "bsms_ipc_close", "bsms_halo_exchange",
     "bsms_encode_in", "bsms_dense128_packed_bytes", "bsms_dense128_pack", "bsms_dense128_stack", "bsms_decode_out",
 ]
 
@@ -89,7 +98,13 @@ def _load():
     lib.bsms_dense128_packed_bytes.argtypes = [i32]
     lib.bsms_dense128_pack.argtypes = [P(vp), i32, i32, vp, vp]
     lib.bsms_dense128_stack.argtypes = [vp, i64, P(vp), P(vp), i32, i32, i32, i32, vp, vp, vp, vp]
-    lib.bsms_decode_out.argtypes = [vp, i64, i32, i32, vp, vp, P(f64), P(f64), vp, vp, vp, vp, vp, vp]
+    lib.bsms_decode_out.argtypes = [vp, i64, i32, i32, vp, vp, P(f64), P(f64), vp, vp, vp, vp, vp, i32, vp]
+    lib.bsms_ipc_alloc.argtypes = [sz, P(vp)]
+    lib.bsms_ipc_free.argtypes = [vp]
+    lib.bsms_ipc_export.argtypes = [vp, C.c_char_p]
+    lib.bsms_ipc_open.argtypes = [C.c_char_p, P(vp)]
+    lib.bsms_ipc_close.argtypes = [vp]
+    lib.bsms_halo_exchange.argtypes = [P(HaloArgsC), vp]
     lib.bsms_prof_enable.argtypes = [C.c_int]
     lib.bsms_prof_collect.argtypes = [P(C.c_double), P(i64), C.c_int]
     for name in EXPORTS:

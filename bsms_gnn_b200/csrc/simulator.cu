@@ -70,6 +70,7 @@ struct DecodeParams {
   float* pred;           // [rows, C]
   float* next_in;        // [rows, Cin] or null
   int Cin, C;
+  int pos_feedback;  // next_in's position channels receive the new state (deforming meshes, C == P)
   long long rows;
 };
 
@@ -90,14 +91,15 @@ __global__ void __launch_bounds__(256) k_decode_out(const DecodeParams p) {
     const float mk = p.mask[r];
     if (lane < p.Cin) {
       float v = in[lane];  // pos / type channels pass through
-      if (lane < p.C) {
+      const int ci = lane < p.C ? lane : ((p.pos_feedback && lane < 2 * p.C) ? lane - p.C : -1);
+      if (ci >= 0) {
         float oc = 0.f;
 #pragma unroll
-        for (int c = 0; c < kMaxOut; ++c) oc = lane == c ? o[c] : oc;
+        for (int c = 0; c < kMaxOut; ++c) oc = ci == c ? o[c] : oc;
         // Normalizer.inverse (normalizer.py:80-83): fp64 product, cast to fp32; then mask and residual (model.py:158-163)
-        const float delta = (float)((double)(oc + p.b3[lane]) * p.std[lane] + p.mean[lane]);
-        v = in[lane] + delta * mk;
-        p.pred[r * p.C + lane] = v;
+        const float delta = (float)((double)(oc + p.b3[ci]) * p.std[ci] + p.mean[ci]);
+        v = in[ci] + delta * mk;
+        if (lane < p.C) p.pred[r * p.C + lane] = v;
       }
       if (p.next_in) p.next_in[r * p.Cin + lane] = (p.ic && mk == 0.f) ? p.ic[r * p.Cin + lane] : v;  // rollout_utils.py:57-62
     }
@@ -154,7 +156,7 @@ extern "C" int bsms_encode_in(const float* node_in, int64_t rows, int32_t Cin, i
 
 extern "C" int bsms_decode_out(const float* y, int64_t rows, int32_t Cin, int32_t C, const float* W3, const float* b3,
                                const double* mean_host, const double* std_host, const float* node_in, const float* mask,
-                               const float* ic, float* pred, float* next_in, void* stream) {
+                               const float* ic, float* pred, float* next_in, int32_t pos_feedback, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   BSMS_CHECK_ARG(y && W3 && b3 && mean_host && std_host && node_in && mask && pred && rows >= 1, "bsms_decode_out: null argument");
   BSMS_CHECK_ARG(C >= 1 && C <= kMaxOut && Cin > C && Cin <= 32, "bsms_decode_out: out_dim %d unsupported (1..%d)", C, kMaxOut);
@@ -171,6 +173,8 @@ extern "C" int bsms_decode_out(const float* y, int64_t rows, int32_t Cin, int32_
   p.ic = ic;
   p.pred = pred;
   p.next_in = next_in;
+  p.pos_feedback = pos_feedback;
+  BSMS_CHECK_ARG(!pos_feedback || Cin == 2 * C + 1, "bsms_decode_out: pos_feedback needs pos_dim == out_dim");
   p.Cin = Cin;
   p.C = C;
   p.rows = rows;

@@ -228,14 +228,31 @@ def exchange_requests(plan, group=None):
 
 # ------------------------------------------------------------------------------------------ the schedule
 class PartitionedBSGMP(torch.nn.Module):
-    def __init__(self, model: BSGMP, plans, exchanger, device=None):
+    def __init__(self, model: BSGMP, plans, exchanger, device=None, pos_exchanger=None):
         super().__init__()
         self.model = model
         device = device or next(model.parameters()).device
         self.states = [RankState(p, device) for p in plans]
         self.ex = exchanger
         self.depth = model.unet_depth
+        # positions of a static mesh are exchanged once (cached): they may travel over a different exchanger than
+        # the features (the push exchanger lays out one buffer per feature call site)
+        self.ex_pos = pos_exchanger or exchanger
+        if hasattr(exchanger, "setup") and not exchanger.ready:
+            exchanger.setup(self.states[0], self.site_levels(), 128)
         self._pos_key, self._pos_cache, self._pos_ref = None, None, None
+
+    def site_levels(self):
+        """Level of every feature exchange of one forward, in call order (4·depth + 1 sites)."""
+        d = self.depth
+        seq = []
+        for l in range(d):
+            seq += [l, l]
+        seq.append(d)
+        for k in range(d):
+            l = d - 1 - k
+            seq += [l + 1, l]
+        return seq
 
     @staticmethod
     def _gmp(gmp, x_loc, lv, p_loc):
@@ -265,7 +282,7 @@ class PartitionedBSGMP(torch.nn.Module):
         # the key is only meaningful while the tensors it was taken from are alive: keep them, otherwise the
         # caching allocator can hand the same address (and version 0) to a DIFFERENT position tensor
         self._pos_ref = list(pos_own)
-        d, S, ex = self.depth, self.states, self.ex
+        d, S, ex = self.depth, self.states, self.ex_pos
         R = range(len(S))
         with torch.no_grad():
             p = [t.detach().to(torch.float32).contiguous() for t in pos_own]
@@ -283,6 +300,8 @@ class PartitionedBSGMP(torch.nn.Module):
         R = range(len(S))
         x = [t.contiguous() for t in h_own]
         pos_loc = self._positions(pos_own)
+        if hasattr(ex, "begin"):
+            ex.begin()
         skips = []
         for l in range(d):
             x_loc, p_loc = ex.exchange(S, l, x), pos_loc[l]

@@ -30,8 +30,9 @@ def _darr(vals):
 
 
 class FusedSimulator:
-    def __init__(self, model, mode=None):
+    def __init__(self, model, mode=None, pos_feedback=False):
         self.model = model
+        self.pos_feedback = bool(pos_feedback)  # deforming meshes: the next input's mesh positions are the new state
         self.process = model.process
         if mode is not None:
             self.process.set_mode(mode)
@@ -110,7 +111,8 @@ class FusedSimulator:
         icc = None if ic is None else ic.contiguous().float()
         with torch.cuda.device(dev):
             check(lib.bsms_decode_out(ptr(y), rows, self.Cin, self.C, ptr(self.dec[3].weight), ptr(self.dec[3].bias),
-                                      self.out_mean, self.out_std, ptr(x), ptr(mask), ptr(icc), ptr(pred), ptr(nxt), stream_ptr()))
+                                      self.out_mean, self.out_std, ptr(x), ptr(mask), ptr(icc), ptr(pred), ptr(nxt), int(self.pos_feedback),
+                                      stream_ptr()))
         return (pred, nxt) if want_next else pred
 
     __call__ = forward

@@ -239,7 +239,44 @@ int bsms_dense128_stack(const float* x, int64_t rows, const float* const* W_host
  * next_in = mask == 0 ? ic : [pred | pos | type]  (rollout_utils.py:57-62; ic may be NULL). */
 int bsms_decode_out(const float* y, int64_t rows, int32_t Cin, int32_t C, const float* W3, const float* b3,
                     const double* mean_host, const double* std_host, const float* node_in,
-                    const float* mask, const float* ic, float* pred, float* next_in, void* stream);
+                    const float* mask, const float* ic, float* pred, float* next_in,
+                    int32_t pos_feedback /* deforming meshes (pos_dim == out_dim): next_in's position channels
+                                            receive the new state instead of passing through */,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K6: halo exchange of the node-partitioned processor (one process per GPU of one NVLink box) as
+ * ONE kernel per exchange over peer-mapped memory.  The reference has no partitioning; this is the
+ * exchange step SURVEY.md §8e derives: before every operator that reads neighbours the ghost rows
+ * of a level are refreshed from their owners, and the adjoint returns ghost gradients in backward.
+ * Arenas come from bsms_ipc_alloc (cudaMalloc, zero-filled) and are mapped into the peers with
+ * bsms_ipc_export / bsms_ipc_open (CUDA IPC, 64-byte handles, host pointers).
+ * ------------------------------------------------------------------------------------------- */
+int bsms_ipc_alloc(size_t bytes, void** ptr_out_host);
+int bsms_ipc_free(void* ptr);
+int bsms_ipc_export(void* ptr, uint8_t* handle64_host);
+int bsms_ipc_open(const uint8_t* handle64_host, void** ptr_out_host);
+int bsms_ipc_close(void* ptr);
+
+typedef struct bsms_halo_args {
+  int32_t world, rank, channels /* floats per row, multiple of 4 */, backward;
+  int64_t n_own, n_ghost, n_send;
+  const float* src;         /* forward: x_own [n_own, C];  backward: g_local [n_own + n_ghost, C]        */
+  float* dst;               /* forward: out [n_own + n_ghost, C] IN THIS RANK'S ARENA (peers write its ghost
+                               rows); backward: g_own [n_own, C]                                          */
+  const int64_t* send_idx;  /* [n_send] owned rows this rank sends, grouped by destination peer (device)  */
+  int32_t send_off[9];      /* [world + 1] row offsets of the groups of send_idx                          */
+  int32_t recv_off[9];      /* [world + 1] row offsets of this rank's ghost rows, grouped by owner        */
+  void* peer_dst[8];        /* forward: where my rows start in peer q's out buffer; backward: where my ghost
+                               gradients start in owner q's `back` region (peer-mapped device pointers)    */
+  const float* back;        /* backward: this rank's own `back` region [n_send, C] (peers write it)       */
+  void* my_flags;           /* uint32[world] in this rank's arena: slot q is written by peer q            */
+  void* peer_flag[8];       /* address of slot [rank] inside peer q's flags of the same call site         */
+  void* ctrl;               /* uint32[4] in this rank's arena, zero-initialised: epoch + arrive counters  */
+} bsms_halo_args;
+/* One exchange (see above).  Asynchronous on `stream`, CUDA-graph capturable; returns when launched.
+ * Every rank of the group must call it for the same call site in the same order. */
+int bsms_halo_exchange(const bsms_halo_args* args, void* stream);
 
 /* Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline pass).
  * Kinds: 0 edge-MLP forward GEMM/chain, 1 node-level forward GEMMs, 2 edge gather+combine,

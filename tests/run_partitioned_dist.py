@@ -19,6 +19,8 @@ def main():
     ap.add_argument("--nx", type=int, default=120)
     ap.add_argument("--depth", type=int, default=4)
     ap.add_argument("--mode", default="fp32")
+    ap.add_argument("--exchange", default="push", choices=["push", "nccl"])
+    ap.add_argument("--steps", type=int, default=2, help="repeat the step: the push exchanger reuses its buffers / epochs")
     a = ap.parse_args()
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
@@ -39,11 +41,19 @@ def main():
     h = torch.randn(n0, 128, generator=torch.Generator().manual_seed(2)).to(dev)
     post = torch.from_numpy(pos).to(dev)
     plan = exchange_requests(partition.build_rank_plan(m_gs, m_ids, n0, world, rank))
-    pm = PartitionedBSGMP(model, [plan], DistExchanger(), dev)
+    if a.exchange == "push":
+        from bsms_gnn_b200.halo import PushExchanger
+        pm = PartitionedBSGMP(model, [plan], PushExchanger(), dev, pos_exchanger=DistExchanger())
+    else:
+        pm = PartitionedBSGMP(model, [plan], DistExchanger(), dev)
     own = torch.from_numpy(plan.levels[0].nodes[:plan.levels[0].n_own]).to(dev)
-    (out_own,) = pm([h[own]], [post[own]])
-    (out_own.square().sum() / h.numel()).backward()
-    GradBucket(list(model.parameters())).step_sync()
+    bucket = GradBucket(list(model.parameters()))
+    p_own = post[own]
+    for _ in range(a.steps):  # every step ends in the all-reduce (the barrier the buffer reuse relies on)
+        model.zero_grad()
+        (out_own,) = pm([h[own]], [p_own])
+        (out_own.square().sum() / h.numel()).backward()
+        bucket.step_sync()
     part_grads = {k: v.grad.clone() for k, v in model.named_parameters()}
     full = torch.zeros_like(h)
     full[own] = out_own.detach()
@@ -56,7 +66,7 @@ def main():
         e_f = max_rel(full, ref.detach())
         e_g = max(max_rel(part_grads[k], v.grad) for k, v in model.named_parameters())
         ghosts = [lv.n_local - lv.n_own for lv in pm.states[0].levels]
-        print(f"partitioned x{world} ({n0} nodes, depth {a.depth}, {a.mode}): forward max-rel {e_f:.2e}, "
+        print(f"partitioned x{world} [{a.exchange}] ({n0} nodes, depth {a.depth}, {a.mode}, {a.steps} steps): forward max-rel {e_f:.2e}, "
               f"param-grad max-rel {e_g:.2e}; rank-0 ghosts per level {ghosts}")
         ok = e_f < 1e-5 and e_g < 5e-4 if a.mode != "bf16" else e_f < 3e-2
     flag = torch.tensor([1 if ok else 0], device=dev)
