@@ -284,7 +284,21 @@ def measure_mesh(args, rank, world, local_rank, dev, nx, depth, steps, warmup, w
         t = torch.tensor([ms, e2e_s * 1e3], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1]) / 1e3
-    res = {"ms_per_step": ms, "e2e_ms_per_step": e2e_s * 1e3, "launches_per_step": int(launches_per_step), "ghosts": ghosts,
+    kinds = None
+    if args.prof:
+        # per-kernel-class device time of one EAGER step (library profiler, CUDA events): where the partitioned step
+        # spends its time — "transfer" contains the halo kernels, whose duration includes waiting for the slowest peer
+        barrier()
+        if rank == 0:
+            _lib.prof_enable(True)
+        for _ in range(2):
+            step(h_dev)
+        barrier()
+        if rank == 0:
+            prof = _lib.prof_collect()
+            _lib.prof_enable(False)
+            kinds = {k: {"ms": round(v[0] / 2, 3), "launches": v[1] // 2} for k, v in prof.items() if v[1]}
+    res = {"kinds": kinds, "ms_per_step": ms, "e2e_ms_per_step": e2e_s * 1e3, "launches_per_step": int(launches_per_step), "ghosts": ghosts,
            "setup_s": setup_s, "n0": n0, "E0": E0, "edge_rows": edge_rows, "clocks": cs.result, "exchange": exchange,
            "h2d_bytes_per_step": int(h_host.numel() * 4), "graph": graph, "single_ms_per_step": None}
     if want_single and world > 1:
@@ -344,7 +358,7 @@ def run_mesh(args):
                        "rank0_ghost_rows_per_level": r["ghosts"], "setup_s": r["setup_s"],
                        "l2": "per-step working set far exceeds the 126 MB L2"},
             "edge_evals_per_s": r["edge_rows"] / (ms * 1e-3),
-            "single_gpu_ms_per_step_same_run": r["single_ms_per_step"],
+            "single_gpu_ms_per_step_same_run": r["single_ms_per_step"], "kernel_breakdown_eager": r["kinds"],
             "speedup_vs_single_gpu_same_run": (r["single_ms_per_step"] / ms) if r["single_ms_per_step"] else None,
             "clocks": {"sm_mhz": clk.get("sm_mhz"), "sm_max_mhz": clk.get("sm_max_mhz"), "reasons": clk.get("reasons")},
             "e2e": {"value": E0 / (r["e2e_ms_per_step"] * 1e-3) / 1e6, "unit": "M-edges/s", "h2d_bytes_per_step": r["h2d_bytes_per_step"],
@@ -398,6 +412,10 @@ class _SimModel(torch.nn.Module):
 
 
 def run_rollout(args):
+    print(json.dumps(measure_rollout(args, args.mesh, args.mode, args.steps if args.steps != 10 else 599, args.warmup)))
+
+
+def measure_rollout(args, mesh, mode, T, warmup):
     """BASELINE.json configs 2 and 4: T sequential whole-model forwards with feedback, B = 1 — the reference's
     rollout_one_traj (src/utils/rollout_utils.py:15-64): encoder -> processor -> decoder, normalisers, mask,
     residual, next input = prediction with the boundary nodes re-imposed.
@@ -408,9 +426,8 @@ def run_rollout(args):
     from bsms_gnn_b200 import _lib, hierarchy, meshgen
     from bsms_gnn_b200.simulator import FusedSimulator, GraphedRollout
 
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
-    if args.mesh == "sphere":
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if mesh == "sphere":
         pos, cells = meshgen.icosphere(5)
         depth, C, P, name = 6, 3, 3, "icosphere-5"
         m_gs, m_ids = hierarchy.build_hierarchy(meshgen.cells_to_flat_edge(cells), depth, pos.shape[0], pos)
@@ -421,21 +438,19 @@ def run_rollout(args):
         C, P, name = 2, 2, f"cylinder-like {nx}x{nx} tri-grid"
     N, E0 = pos.shape[0], int(m_gs[0].shape[1])
     edge_rows = 2 * sum(int(g.shape[1]) for g in m_gs[:depth]) + int(m_gs[depth].shape[1])
-    mode = args.mode
     model = _SimModel(depth, C, P, mode, dev)
-    sim = FusedSimulator(model, mode=mode, pos_feedback=(args.mesh == "sphere"))
+    sim = FusedSimulator(model, mode=mode, pos_feedback=(mesh == "sphere"))
     gs = [torch.from_numpy(g).to(dev) for g in m_gs]
     ids = [torch.from_numpy(i).to(dev) for i in m_ids]
     gen = torch.Generator().manual_seed(3)
     ntype = (torch.rand(1, N, 1, generator=gen) > 0.9).float()
     p0 = torch.from_numpy(pos).unsqueeze(0)
-    state0 = p0.clone() if args.mesh == "sphere" else torch.randn(1, N, C, generator=gen)
+    state0 = p0.clone() if mesh == "sphere" else torch.randn(1, N, C, generator=gen)
     ic = torch.cat([state0, p0, ntype], -1).to(dev)
     mask = (ntype == 0).float().to(dev)
-    T = args.steps if args.steps != 10 else 599
     with torch.no_grad():
         # eager (no graph): python + launch bound
-        for _ in range(args.warmup):
+        for _ in range(warmup):
             sim.rollout(ic, mask, gs, ids, 3)
         torch.cuda.synchronize()
         n0 = _lib.launch_count()
@@ -447,11 +462,11 @@ def run_rollout(args):
         ms_eager = e0.elapsed_time(e1) / min(T, 100)
         launches = (_lib.launch_count() - n0) / min(T, 100)
         gr = GraphedRollout(sim, ic, mask, gs, ids)
-        for _ in range(args.warmup):
+        for _ in range(warmup):
             gr.step()
         gr.reset()
         torch.cuda.synchronize()
-        with ClockSampler(0) as cs:
+        with ClockSampler(dev.index) as cs:
             e0.record()
             res = gr.run(T)
             e1.record()
@@ -468,19 +483,19 @@ def run_rollout(args):
         torch.cuda.synchronize()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / T
     clk = cs.result
-    print(json.dumps({
+    return ({
         "metric": "M-edges/s per BSMS forward (rollout step, whole model)", "value": E0 / (ms_graph * 1e-3) / 1e6, "unit": "M-edges/s",
-        "n_gpus": 1, "steps": T, "warmup": args.warmup, "ms_per_step": ms_graph, "higher_is_better": True,
+        "n_gpus": 1, "steps": T, "warmup": warmup, "ms_per_step": ms_graph, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": mode, "data": "synthetic",
         "config": {"workload": f"{name} ({N} nodes / {E0} directed edges), unet_depth {depth}, out_dim {C}, pos_dim {P}, B=1, "
                                f"rollout of {T} sequential whole-model steps with on-device feedback and boundary re-imposition"
-                               + (", mesh positions updated every step" if args.mesh == "sphere" else ""),
+                               + (", mesh positions updated every step" if mesh == "sphere" else ""),
                    "mode": mode, "execution": "one CUDA graph per step (encoder + processor + decoder + feedback)"},
         "ms_per_step_eager": ms_eager, "ms_per_step_graph": ms_graph, "graph_vs_eager_max_rel": err,
         "edge_evals_per_s": edge_rows / (ms_graph * 1e-3), "gpu_launches": int(launches * T), "kernels_per_step": launches,
         "clocks": {"sm_mhz": clk.get("sm_mhz"), "sm_max_mhz": clk.get("sm_max_mhz"), "reasons": clk.get("reasons")},
         "e2e": {"value": E0 / (e2e_ms * 1e-3) / 1e6, "unit": "M-edges/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 0,
-                "d2h_bytes_per_step": int(N * C * 4), "note": "the input of step k+1 is produced on the device by step k; every state is copied to pinned host memory"}}))
+                "d2h_bytes_per_step": int(N * C * 4), "note": "the input of step k+1 is produced on the device by step k; every state is copied to pinned host memory"}})
 
 
 def main():
@@ -499,6 +514,7 @@ def main():
     ap.add_argument("--no-self-check", action="store_true")
     ap.add_argument("--mesh-nx", type=int, default=1414, help="N > 1: side of the strong-scaling mesh reported in extra.mesh_strong")
     ap.add_argument("--exchange", default="push", choices=["push", "nccl"], help="mesh workload, N > 1: halo exchange implementation")
+    ap.add_argument("--prof", action="store_true", help="mesh workload: per-kernel-class breakdown of one eager step on rank 0")
     ap.add_argument("--single-ref", action="store_true", help="mesh workload, N > 1: rank 0 also times the un-partitioned mesh")
     ap.add_argument("--mesh", default="cylinder", choices=["cylinder", "sphere"], help="rollout workload: config 2 / config 4")
     ap.add_argument("--no-graph", action="store_true", help="mesh workload: run the step eagerly instead of replaying a CUDA graph")
@@ -802,6 +818,18 @@ def main():
                            "gpu_launches_per_step": mr["launches_per_step"],
                            "n1_reference": "the same mesh un-partitioned on rank 0's GPU, eager, CUDA events, same run"}
 
+    # ---- N = 1: BASELINE.json configs 2 and 4 (whole-model rollouts, B = 1) in the same run, short form
+    rollouts = None
+    if world == 1 and os.environ.get("BSMS_BENCH_ROLLOUT", "1") != "0":
+        rollouts = {}
+        for cfg_name, mesh, rmode in (("config2_cylinder_fp16x3", "cylinder", "fp16x3"), ("config2_cylinder_bf16", "cylinder", "bf16"),
+                                      ("config4_sphere_fp16x3", "sphere", "fp16x3"), ("config4_sphere_bf16", "sphere", "bf16")):
+            rr = measure_rollout(args, mesh, rmode, 200, 3)
+            rollouts[cfg_name] = {"workload": rr["config"]["workload"], "mode": rmode, "ms_per_step": rr["ms_per_step_graph"],
+                                  "ms_per_step_eager": rr["ms_per_step_eager"], "kernels_per_step": rr["kernels_per_step"],
+                                  "value": rr["value"], "unit": rr["unit"], "e2e_ms_per_step": rr["e2e"]["ms_per_step"],
+                                  "d2h_bytes_per_step": rr["e2e"]["d2h_bytes_per_step"]}
+
     if rank == 0:
         value = world * B * E0 / (ms * 1e-3) / 1e6
         clk = cs.result
@@ -822,7 +850,7 @@ def main():
                     "ms_per_step": e2e_s * 1e3},
             "gpu_launches": int(launches),
             "roofline": roofline, "roofline_fused_edge_kernel": roofline_edge, "kernel_breakdown": breakdown, "cpu_baseline": cpu,
-            "self_check": self_check, "extra": {"mesh_strong": mesh_strong},
+            "self_check": self_check, "extra": {"mesh_strong": mesh_strong, "rollouts": rollouts},
         }
         print(json.dumps(out), flush=True)
     if world > 1:

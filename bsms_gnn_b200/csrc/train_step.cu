@@ -5,6 +5,7 @@
 // tensor (the reference's 132 tensors -> ~600 launches per step).  Every scalar that changes from step to
 // step (loss sums, gradient norm, step counter, learning rate) lives on the device, so the whole step is
 // free of host synchronisation and CUDA-graph capturable.  All kernels are HBM-bound elementwise passes.
+#include <curand_kernel.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -155,6 +156,34 @@ k_clip_adamw(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m
   }
 }
 
+// ---- training noise of the reference's datapipe (src/datasets/base.py:274-289), on the device: per node and output
+//      channel c, n ~ N(0, noise_level[c]), zero on nodes whose loss mask is 0 (Dirichlet nodes);
+//      node_in[:, c] += n, node_tar[:, c] += (1 - gamma) n.  Philox counter-based stream: (seed, row, offset).
+struct NoiseParams {
+  float* node_in;
+  int Cin;
+  float* node_tar;
+  int C;
+  const float* mask;
+  long long rows;
+  float level[4];
+  float one_minus_gamma;
+  unsigned long long seed, offset;
+};
+__global__ void __launch_bounds__(256) k_inject_noise(const NoiseParams p) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < p.rows; r += (long long)gridDim.x * blockDim.x) {
+    if (p.mask[r] == 0.f) continue;
+    curandStatePhilox4_32_10_t st;
+    curand_init(p.seed, (unsigned long long)r, p.offset, &st);
+    const float4 z = curand_normal4(&st);
+    const float n[4] = {z.x * p.level[0], z.y * p.level[1], z.z * p.level[2], z.w * p.level[3]};
+    for (int c = 0; c < p.C; ++c) {
+      p.node_in[r * p.Cin + c] += n[c];
+      p.node_tar[r * p.C + c] += p.one_minus_gamma * n[c];
+    }
+  }
+}
+
 static int grid_for(long long n, int per_thread) {
   long long b = (n + 256ll * per_thread - 1) / (256ll * per_thread);
   return (int)std::max<long long>(1, std::min<long long>(b, 148 * 8));
@@ -209,5 +238,27 @@ extern "C" int bsms_clip_adamw_step(float* params, float* grads, float* exp_avg,
                                                  (float)eps, (float)weight_decay, zero_grad);
     BSMS_LAUNCHED();
   }
+  return BSMS_OK;
+}
+
+extern "C" int bsms_inject_noise(float* node_in, int32_t Cin, float* node_tar, int32_t C, const float* mask, int64_t rows,
+                                 const float* noise_level_host, float noise_gamma, uint64_t seed, uint64_t offset, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  BSMS_CHECK_ARG(node_in && node_tar && mask && noise_level_host && rows >= 1, "bsms_inject_noise: null argument");
+  BSMS_CHECK_ARG(C >= 1 && C <= 4 && Cin >= C, "bsms_inject_noise: 1..4 output channels");
+  NoiseParams p;
+  p.node_in = node_in;
+  p.Cin = Cin;
+  p.node_tar = node_tar;
+  p.C = C;
+  p.mask = mask;
+  p.rows = rows;
+  for (int c = 0; c < 4; ++c) p.level[c] = c < C ? noise_level_host[c] : 0.f;
+  p.one_minus_gamma = 1.f - noise_gamma;
+  p.seed = seed;
+  p.offset = offset;
+  ProfScope ps_(PK_OTHER, st);
+  k_inject_noise<<<grid_for(rows, 1), 256, 0, st>>>(p);
+  BSMS_LAUNCHED();
   return BSMS_OK;
 }

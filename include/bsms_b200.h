@@ -278,6 +278,14 @@ typedef struct bsms_halo_args {
  * Every rank of the group must call it for the same call site in the same order. */
 int bsms_halo_exchange(const bsms_halo_args* args, void* stream);
 
+/* Training noise of the reference's datapipe on the device (src/datasets/base.py:274-289): per node
+ * and output channel c, n ~ N(0, noise_level[c]) (zero where mask == 0); node_in[:, c] += n,
+ * node_tar[:, c] += (1 - noise_gamma) n.  node_in [rows, Cin], node_tar [rows, C], C <= 4.
+ * Counter-based Philox stream keyed by (seed, row, offset): reproducible, NOT torch's CPU stream. */
+int bsms_inject_noise(float* node_in, int32_t Cin, float* node_tar, int32_t C, const float* mask,
+                      int64_t rows, const float* noise_level_host, float noise_gamma, uint64_t seed,
+                      uint64_t offset, void* stream);
+
 /* Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline pass).
  * Kinds: 0 edge-MLP forward GEMM/chain, 1 node-level forward GEMMs, 2 edge gather+combine,
  * 3 LayerNorm+segment-sum, 4 dgrad, 5 wgrad, 6 LayerNorm backward, 7 edge-gradient segment sums,

@@ -140,7 +140,7 @@ def test_bind_mesh_and_identity_cache():
         model.bind_mesh(gs, ids, pos.shape[0])
         got = model(h, [i.clone() for i in ids], [g.clone() for g in gs], p)  # bound: fresh copies cost nothing
         assert P.STATS["fingerprints"] == f0
-        assert torch.equal(got, want)
+        assert max_rel(got, want) < 2e-6  # the default mode's edge stage reduces with red.add: order varies run to run
         with pytest.raises(RuntimeError):
             model(h[:-1], ids, gs, p[:-1])
         model.unbind_mesh()
