@@ -83,7 +83,9 @@ __device__ __forceinline__ float4 make_fiber(const float* __restrict__ pb, int P
 //    (8.42 vs 7.91 ms: two N = 64 groups re-read the A operand and take longer than one N = 128 group); the
 //    sender-side scatter as 512-byte bulk reductions (UBLKRED, 8.16 vs 7.88 ms: ~30 cycles of issue each); the
 //    gather of tile i+1 interleaved with the scatter rows of tile i (7.75 vs 7.57 ms: loads and reductions share
-//    the SM's L1/L2 port, the merged phase costs the sum of the two).
+//    the SM's L1/L2 port, the merged phase costs the sum of the two); rows 0..63 of the next tile gathered into a
+//    16 KB side buffer inside the shadow of the first data-gradient GEMM (7.75 vs 7.54 ms: the tile start gets
+//    1.3 k cycles shorter, the shadow 1.45 k longer — an MMA pair lasts ~1 k cycles, a batch of gathers ~2 k).
 //  * F2: the epilogue arithmetic uses the packed fp32x2 instructions of sm_100 (FADD2 / FFMA2): the epilogues
 //    are bound by the FMA pipe's issue rate, not by latency.
 template <bool PROF, bool F2>
