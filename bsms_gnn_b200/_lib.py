@@ -48,6 +48,7 @@ EXPORTS = [
     "bsms_gmp_backward", "bsms_launch_count", "bsms_prof_enable", "bsms_prof_collect",
     "bsms_debug_edge_stage", "bsms_masked_rmse", "bsms_clip_adamw_step", "bsms_inject_noise",
     "bsms_gmp_packed_bytes", "bsms_gmp_pack", "bsms_gmp_forward_packed",
+    "bsms_components_host", "bsms_bistride_level_host", "bsms_host_free",
     "bsms_ipc_alloc", "bsms_ipc_free", "bsms_ipc_export", "bsms_ipc_open", "bsms_ipc_close", "bsms_halo_exchange",
     "bsms_encode_in", "bsms_dense128_packed_bytes", "bsms_dense128_pack", "bsms_dense128_stack", "bsms_decode_out",
 ]
@@ -100,6 +101,10 @@ def _load():
     lib.bsms_dense128_pack.argtypes = [P(vp), i32, i32, vp, vp]
     lib.bsms_dense128_stack.argtypes = [vp, i64, P(vp), P(vp), i32, i32, i32, i32, vp, vp, vp, vp]
     lib.bsms_decode_out.argtypes = [vp, i64, i32, i32, vp, vp, P(f64), P(f64), vp, vp, vp, vp, vp, i32, vp]
+    lib.bsms_components_host.argtypes = [vp, i64, i64, vp, P(i64)]
+    lib.bsms_bistride_level_host.argtypes = [vp, i64, i64, vp, i64, vp, vp, P(i64), P(vp), P(i64)]
+    lib.bsms_host_free.argtypes = [vp]
+    lib.bsms_host_free.restype = None
     lib.bsms_ipc_alloc.argtypes = [sz, P(vp)]
     lib.bsms_ipc_free.argtypes = [vp]
     lib.bsms_ipc_export.argtypes = [vp, C.c_char_p]

@@ -1,4 +1,10 @@
-"""Bi-stride multi-level graph builder (vectorised numpy/scipy; once per mesh, off the hot path).
+"""Bi-stride multi-level graph builder (once per mesh, off the hot path).
+
+Two implementations of the same function, both exact against the reference's goldens (tests/test_hierarchy.py):
+`native` (default) — the integer work (clusters, BFS parity, kept-row (A+I)^2, re-indexing) runs in the library's
+host code (csrc/hierarchy_host.cpp, OpenMP; `bsms_components_host`, `bsms_bistride_level_host`), only the
+floating-point seed choice stays in numpy; `numpy` — the vectorised numpy/scipy version below, kept as the
+cross-check.  `BSMS_HIERARCHY=numpy` selects the latter.
 
 Produces the same `(m_gs, m_ids)` the reference builds in pure Python with
 `BistrideMultiLayerGraph(flat_edge, num_layers, num_nodes, pos).get_multi_layer_graphs()`
@@ -62,11 +68,8 @@ def _bfs_levels(a: sp.csr_matrix, seeds: np.ndarray) -> np.ndarray:
     return dist
 
 
-def bistride_level(flat_edge: np.ndarray, pos: np.ndarray, n: int):
-    """One pooling level: returns (kept node ids sorted [n'], new flat edges [2,E'] int64)."""
-    flat_edge = np.asarray(flat_edge, dtype=np.int64).reshape(2, -1)
-    a = _csr_pattern(flat_edge, n)
-    ncomp, labels = connected_components(a, directed=True, connection="weak")
+def _cluster_seeds(labels: np.ndarray, ncomp: int, pos: np.ndarray) -> np.ndarray:
+    """Per cluster the node nearest the cluster centroid (bsms_graph_wrapper.py:107-126), numpy arithmetic."""
     # clusters ordered by their smallest node id, members ascending (graph_wrapper.py:107-134)
     order = np.argsort(labels, kind="stable")
     bounds = np.concatenate([[0], np.cumsum(np.bincount(labels, minlength=ncomp))])
@@ -80,6 +83,45 @@ def bistride_level(flat_edge: np.ndarray, pos: np.ndarray, n: int):
         center = np.mean(pc, axis=0)
         d = np.linalg.norm(pc - center[None, :], 2, axis=-1)
         seeds[c] = members[np.argmin(d)]
+    return seeds
+
+
+def bistride_level_native(flat_edge: np.ndarray, pos: np.ndarray, n: int):
+    """One pooling level through the library's host code; same result as `bistride_level_numpy`."""
+    import ctypes as C
+
+    from ._lib import check, lib
+    fe = np.ascontiguousarray(np.asarray(flat_edge, dtype=np.int64).reshape(2, -1))
+    E = int(fe.shape[1])
+    labels = np.empty(n, dtype=np.int64)
+    ncomp = C.c_int64()
+    check(lib.bsms_components_host(fe.ctypes.data, E, n, labels.ctypes.data, C.byref(ncomp)))
+    seeds = np.ascontiguousarray(_cluster_seeds(labels, int(ncomp.value), pos))
+    keep = np.empty(n, dtype=np.int64)
+    nk, ne, eptr = C.c_int64(), C.c_int64(), C.c_void_p()
+    check(lib.bsms_bistride_level_host(fe.ctypes.data, E, n, labels.ctypes.data, int(ncomp.value), seeds.ctypes.data,
+                                       keep.ctypes.data, C.byref(nk), C.byref(eptr), C.byref(ne)))
+    try:
+        buf = (C.c_int64 * max(2 * ne.value, 1)).from_address(eptr.value)
+        new_e = np.frombuffer(buf, dtype=np.int64, count=2 * ne.value).reshape(2, ne.value).copy()
+    finally:
+        lib.bsms_host_free(eptr)
+    return keep[:nk.value].copy(), new_e
+
+
+def bistride_level(flat_edge: np.ndarray, pos: np.ndarray, n: int):
+    import os
+    if os.environ.get("BSMS_HIERARCHY", "native") == "numpy":
+        return bistride_level_numpy(flat_edge, pos, n)
+    return bistride_level_native(flat_edge, pos, n)
+
+
+def bistride_level_numpy(flat_edge: np.ndarray, pos: np.ndarray, n: int):
+    """One pooling level: returns (kept node ids sorted [n'], new flat edges [2,E'] int64)."""
+    flat_edge = np.asarray(flat_edge, dtype=np.int64).reshape(2, -1)
+    a = _csr_pattern(flat_edge, n)
+    ncomp, labels = connected_components(a, directed=True, connection="weak")
+    seeds = _cluster_seeds(labels, ncomp, pos)
     dist = _bfs_levels(a, seeds)
     reach = dist >= 0
     even = reach & (dist % 2 == 0)

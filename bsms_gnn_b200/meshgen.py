@@ -29,8 +29,9 @@ def cells_to_flat_edge(cells: np.ndarray) -> np.ndarray:
         raise ValueError(f"unsupported cell width {k}")
     s = pairs.max(1)
     r = pairs.min(1)
-    uniq = np.unique(np.stack([s, r], 1), axis=0)
-    s, r = uniq[:, 0], uniq[:, 1]
+    base = int(cells.max()) + 1
+    key = np.unique(s * base + r)  # lexicographic in (s, r), like the reference's row-wise unique
+    s, r = key // base, key % base
     return np.stack([np.concatenate([s, r]), np.concatenate([r, s])]).astype(np.int64)
 
 

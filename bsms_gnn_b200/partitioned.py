@@ -35,6 +35,9 @@ class LocalLevel:
         self.n_own, self.n_local = lp.n_own, lp.n_local
         # a rank can own nothing at a deep level (e.g. 52 nodes over 8 ranks): no plan, operators return empties
         self.plan = LevelPlan(t(lp.edges, torch.int64), lp.n_local) if lp.n_local > 0 else None
+        # the GMP aggregates onto OWNED receivers only: its plan holds the receiver-owned edges (no redundant edge rows)
+        self.plan_gmp = (LevelPlan(t(lp.edges[:, np.asarray(lp.gmp_sel, dtype=bool)], torch.int64), lp.n_local)
+                         if lp.n_local > 0 else None)
         self.recv_counts = [int(c) for c in lp.recv_counts]
         self.send_idx = [t(s, torch.int64) for s in lp.send_idx]
         self.send_counts = [int(s.numel()) for s in self.send_idx]
@@ -258,7 +261,7 @@ class PartitionedBSGMP(torch.nn.Module):
     def _gmp(gmp, x_loc, lv, p_loc):
         if lv.plan is None:
             return x_loc[:0]
-        return gmp._run(x_loc, lv.plan, p_loc)[:lv.n_own]
+        return gmp._run(x_loc, lv.plan_gmp, p_loc)[:lv.n_own]
 
     @staticmethod
     def _restrict(x_loc, lv):

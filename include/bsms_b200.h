@@ -286,6 +286,26 @@ int bsms_inject_noise(float* node_in, int32_t Cin, float* node_tar, int32_t C, c
                       int64_t rows, const float* noise_level_host, float noise_gamma, uint64_t seed,
                       uint64_t offset, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Native bi-stride hierarchy builder, HOST code (OpenMP): the integer part of the reference's
+ * BistrideMultiLayerGraph (src/graph_wrappers/bsms_graph_wrapper.py:58-154,
+ * src/graph_wrappers/graph_wrapper.py:67-134).  All pointers are HOST pointers; flat_edge is the
+ * reference's int64 [2, E] list.  Exact (integer) results.
+ * ------------------------------------------------------------------------------------------- */
+/* labels_out[n]: weakly connected cluster of every node, clusters numbered by their smallest node. */
+int bsms_components_host(const int64_t* flat_edge, int64_t n_edges, int64_t n_nodes,
+                         int64_t* labels_out, int64_t* n_comp_out);
+/* One pooling level: BFS parity from one seed per cluster (seeds chosen by the caller: the node
+ * nearest the cluster centroid, bsms_graph_wrapper.py:107-126), keep the smaller parity class,
+ * new edges = pattern of (A+I)^2 minus the diagonal on the kept nodes, re-indexed, row-major with
+ * sorted columns.  keep_out: capacity n_nodes; *edges_out: malloc'ed int64 [2, *n_edges_out],
+ * release with bsms_host_free. */
+int bsms_bistride_level_host(const int64_t* flat_edge, int64_t n_edges, int64_t n_nodes,
+                             const int64_t* labels, int64_t n_comp, const int64_t* seeds,
+                             int64_t* keep_out, int64_t* n_keep_out, int64_t** edges_out,
+                             int64_t* n_edges_out);
+void bsms_host_free(void* p);
+
 /* Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline pass).
  * Kinds: 0 edge-MLP forward GEMM/chain, 1 node-level forward GEMMs, 2 edge gather+combine,
  * 3 LayerNorm+segment-sum, 4 dgrad, 5 wgrad, 6 LayerNorm backward, 7 edge-gradient segment sums,

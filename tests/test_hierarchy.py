@@ -57,3 +57,32 @@ def test_mesh_sizes():
         assert pos.shape == (n, 2) and meshgen.cells_to_flat_edge(cells).shape == (2, e)
     pos, cells = meshgen.icosphere(2)
     assert pos.shape == (162, 3) and meshgen.cells_to_flat_edge(cells).shape == (2, 960)
+
+
+def test_native_builder_equals_numpy_builder(monkeypatch):
+    """csrc/hierarchy_host.cpp against the numpy/scipy implementation: identical ids and identical edge ARRAYS (both
+    emit row-major edges with sorted columns), on a mesh larger than the goldens and on disconnected / directed inputs."""
+    cases = []
+    pos, cells = meshgen.tri_grid(120, 90)
+    cases.append((pos, meshgen.cells_to_flat_edge(cells), 5))
+    pos, cells = meshgen.icosphere(4)
+    cases.append((pos, meshgen.cells_to_flat_edge(cells), 4))
+    p1, c1 = meshgen.tri_grid(9, 7)
+    p2, c2 = meshgen.tri_grid(5, 6, seed=1)
+    cases.append((np.concatenate([p1, p2 + 20, np.array([[99.0, 99.0]], dtype=np.float32)]),
+                  meshgen.cells_to_flat_edge(np.concatenate([c1, c2 + p1.shape[0]])), 3))  # + one isolated node
+    for pos, fe, d in cases:
+        monkeypatch.setenv("BSMS_HIERARCHY", "numpy")
+        gs_n, ids_n = hierarchy.build_hierarchy(fe, d, pos.shape[0], pos)
+        monkeypatch.setenv("BSMS_HIERARCHY", "native")
+        gs_c, ids_c = hierarchy.build_hierarchy(fe, d, pos.shape[0], pos)
+        for a, b in zip(ids_c, ids_n):
+            assert np.array_equal(a, b)
+        for a, b in zip(gs_c[1:], gs_n[1:]):
+            assert np.array_equal(a, b)
+    # a one-directional chain: nodes the seed cannot reach are in neither parity class
+    fe = np.array([[0, 1, 2, 3], [1, 2, 3, 4]])
+    pos = np.stack([np.arange(5.0), np.zeros(5)], 1).astype(np.float32)
+    k_n, e_n = hierarchy.bistride_level_numpy(fe, pos, 5)
+    k_c, e_c = hierarchy.bistride_level_native(fe, pos, 5)
+    assert np.array_equal(k_n, k_c) and np.array_equal(e_n, e_c)

@@ -38,7 +38,7 @@ def emulate(plans, params, h, pos, d):
         y_own = []
         for r in range(R):
             lp = plans[r].levels[l]
-            y_own.append(O.gmp(x_loc[r], T(lp.edges), p_loc[r], params, f"down_gmps.{l}")[:lp.n_own])
+            y_own.append(O.gmp(x_loc[r], T(lp.edges[:, lp.gmp_sel]), p_loc[r], params, f"down_gmps.{l}")[:lp.n_own])
         skips.append(y_own)
         y_loc = exchange(l, y_own)
         x_own, p_own = [], []
@@ -48,8 +48,8 @@ def emulate(plans, params, h, pos, d):
             x_own.append(O.edge_conv(y_loc[r], e, ew)[ids])
             p_own.append(O.edge_conv(p_loc[r], e, ew)[ids])
     x_loc, p_loc = exchange(d, x_own), exchange(d, p_own)
-    x_own = [O.gmp(x_loc[r], T(plans[r].levels[d].edges), p_loc[r], params, "bottom_gmp")[:plans[r].levels[d].n_own]
-             for r in range(R)]
+    x_own = [O.gmp(x_loc[r], T(plans[r].levels[d].edges[:, plans[r].levels[d].gmp_sel]), p_loc[r], params,
+                   "bottom_gmp")[:plans[r].levels[d].n_own] for r in range(R)]
     for k in range(d):
         l = d - 1 - k
         hc_loc = exchange(l + 1, x_own)
@@ -62,8 +62,8 @@ def emulate(plans, params, h, pos, d):
             U[kept] = hc_loc[r][inv[kept]]
             u_own.append(O.edge_conv(U, T(lp.edges), T(lp.ew), aggragating=False)[:lp.n_own])
         u_loc = exchange(l, u_own)
-        x_own = [O.gmp(u_loc[r], T(plans[r].levels[l].edges), pos_loc[l][r], params, f"up_gmps.{k}")[:plans[r].levels[l].n_own]
-                 + skips[l][r] for r in range(R)]
+        x_own = [O.gmp(u_loc[r], T(plans[r].levels[l].edges[:, plans[r].levels[l].gmp_sel]), pos_loc[l][r], params,
+                       f"up_gmps.{k}")[:plans[r].levels[l].n_own] + skips[l][r] for r in range(R)]
     out = torch.zeros_like(h)
     for r in range(R):
         lp = plans[r].levels[0]
@@ -87,6 +87,8 @@ def test_partitioned_schedule_equals_global(hname, world):
         for p in plans:
             lp = p.levels[l]
             assert lp.recv_counts.sum() == lp.n_local - lp.n_own
+        # the receiver-owned edge subsets of all ranks partition the level's edges: no edge-MLP row is computed twice
+        assert sum(int(p.levels[l].gmp_sel.sum()) for p in plans) == gs[l].shape[1]
     ew = partition.cal_ew_global(gs, ids, n0)
     w = torch.ones(n0, 1)
     for l in range(d):
