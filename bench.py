@@ -17,6 +17,7 @@ and the parameter gradients are all-reduced over NCCL once per step.
 bounded sample of the same workload.
 """
 import argparse
+import datetime
 import json
 import os
 import statistics
@@ -338,7 +339,7 @@ def run_mesh(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     nx = args.nx if args.nx != 72 else 1414
     depth = args.depth
     r = measure_mesh(args, rank, world, local_rank, dev, nx, depth, args.steps, args.warmup, want_single=args.single_ref)
@@ -579,7 +580,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     B = args.batch
     model = BSGMP(args.depth, D, 3, 2, mode=args.mode).to(dev)
     model.load_state_dict(O.init_params(args.depth, pos_dim=2, seed=0))
@@ -762,7 +763,11 @@ def main():
     self_check = None
     if rank == 0 and not args.no_self_check:
         from tests.util import l2_rel, max_rel
-        step(h_dev, pos_dev)
+        # rank-local: NO collective may run here (the other ranks are already past this point)
+        for q in params:
+            q.grad = None
+        h_dev.grad = None
+        model(h_dev, ids, gs, pos_dev).square().mean().backward()
         torch.cuda.synchronize()
         gs_c = [torch.from_numpy(g) for g in m_gs]
         ids_c = [torch.from_numpy(i) for i in m_ids]
