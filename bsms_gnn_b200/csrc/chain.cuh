@@ -134,6 +134,27 @@ __device__ __forceinline__ void coop_rows_store(uint8_t* tile, int r_begin, int 
   }
 }
 
+// the same rows as a two-way bf16 split: hi = bf16(v) -> tile_hi, lo = bf16(v - hi) -> tile_lo
+template <int NR>
+__device__ __forceinline__ void coop_rows_store_split(uint8_t* tile_hi, uint8_t* tile_lo, int r_begin, int lane, const float4 (&v)[NR]) {
+  const uint32_t col_off = (uint32_t)((lane >> 4) * 16384 + (lane & 1) * 8);
+  const int chunk7 = (lane >> 1) & 7;
+#pragma unroll
+  for (int u = 0; u < NR; ++u) {
+    const int r = r_begin + u;
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[u].x, v[u].y), h1 = __floats2bfloat162_rn(v[u].z, v[u].w);
+    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    uint2 ph, pl;
+    ph.x = *reinterpret_cast<const uint32_t*>(&h0);
+    ph.y = *reinterpret_cast<const uint32_t*>(&h1);
+    pl.x = pack_bf16(v[u].x - f0.x, v[u].y - f0.y);
+    pl.y = pack_bf16(v[u].z - f1.x, v[u].w - f1.y);
+    const uint32_t off = col_off + r * 128 + ((chunk7 ^ (r & 7)) << 4);
+    *reinterpret_cast<uint2*>(tile_hi + off) = ph;
+    *reinterpret_cast<uint2*>(tile_lo + off) = pl;
+  }
+}
+
 struct PackList {
   const float* w[12];
   int ld[12];
@@ -146,13 +167,18 @@ __global__ void k_pack_weights(PackList pl, uint8_t* __restrict__ out) {
   const int blk = blockIdx.x;
   const float* W = pl.w[blk];
   const int ld = pl.ld[blk];
-  uint8_t* o = out + (size_t)blk * NSPLIT * kWBlk;
+  uint8_t* o = out + (size_t)blk * (NSPLIT == 1 ? 1 : 2) * kWBlk;
   for (int idx = threadIdx.x; idx < 128 * 128; idx += blockDim.x) {
     int n = idx >> 7, k = idx & 127;
     float v = W[(size_t)n * ld + k];
     uint32_t off = wblk_offset(n, k);
     if (NSPLIT == 1) {
       *reinterpret_cast<__nv_bfloat16*>(o + off) = __float2bfloat16_rn(v);
+    } else if (NSPLIT == 3) {
+      // two-way bf16 split, no scaling (bf16 has fp32's exponent range): 16 significant bits, for the gradient GEMMs
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      *reinterpret_cast<__nv_bfloat16*>(o + off) = hi;
+      *reinterpret_cast<__nv_bfloat16*>(o + kWBlk + off) = __float2bfloat16_rn(v - __bfloat162float(hi));
     } else {
       float s = v * kWScale;
       __half hi = __float2half_rn(s);

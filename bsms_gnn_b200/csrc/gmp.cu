@@ -10,6 +10,9 @@
 // per-edge work of layer 0 is a gather-add of two projected rows plus a (P+1)-term fiber FMA.
 // That removes 2*128*128*2 of the 164 608 FLOP/edge and turns the layer-0 weight gradient into
 // a node-level GEMM.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "gemm_fp32.cuh"
 
@@ -44,7 +47,7 @@ k_edge_combine(const float* __restrict__ PsPd, const float* __restrict__ pos, in
   const int ldw = 2 * D + P + 1;
   float4 ps = ld4(PsPd + ((size_t)b * N + i) * 256 + lane * 4);
   float4 pd = ld4(PsPd + ((size_t)b * N + j) * 256 + 128 + lane * 4);
-  float4 bb = ld4(b1 + lane * 4);
+  float4 bb = b1 ? ld4(b1 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);  // null: b1 is already folded into the Pd half
   float v[4] = {ps.x + pd.x + bb.x, ps.y + pd.y + bb.y, ps.z + pd.z + bb.z, ps.w + pd.w + bb.w};
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -283,6 +286,138 @@ int gmp_backward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const 
                     int pos_batched, const float* saved, const float* g_out, float* g_x, const bsms_gmp_grads* gr, int B,
                     int P, void* ws, size_t ws_bytes, cudaStream_t st);
 
+// tensor-core launchers of node_gemm.cu in the two-way bf16 split arithmetic
+struct PackList;
+struct WgradParams;
+int lin_tc2_split(const float* X0, int ldx0, int NB, const uint8_t* const* blocks, int b_mn, const float* bias, int relu,
+                  const float* mask, int ldmask, const float* add0, int ldadd0, const float* add1, int ldadd1, float* Y0,
+                  int ldy0, float* Y1, int ldy1, long long rows, int kind, cudaStream_t st);
+int pack_blocks_bf16split_ptrs(const float* const* W, const int* ld, int n, uint8_t* out, cudaStream_t st);
+int wgrad_tc_split3(const float* const* G, const int* ldg, const float* const* X, const int* ldx, float* const* dW, const int* ldo,
+                    float* const* db, int nprob, long long rows, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------------------------------
+// Backward of the fp32-parity tensor-core mode (BSMS_MODE_FP16X3) ON TENSOR CORES.  Every GEMM of the backward — the
+// recomputation of the three edge layers, the six data gradients and the eleven weight gradients — runs as tcgen05
+// MMAs over two-way bf16 splits of both operands (16 significant bits, fp32's exponent range: gradients of any
+// magnitude; three MMAs per K step), with fp32 accumulation and fp32 tensors in HBM.  Per-edge activations are
+// recomputed into the workspace (never kept between forward and backward); the node-level tensors come from
+// `saved`.  Non-GEMM kernels (gather/combine, LayerNorm backward, segment sums) are the exact-fp32 ones of the
+// fp32 mode.  Reference: src/ops/basic.py:48-98 differentiated by autograd.
+static int backward_x3(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos, int pos_batched,
+                       const float* saved, const float* g_out, float* g_x, const bsms_gmp_grads* gr, int B, int P, void* ws,
+                       size_t ws_bytes, cudaStream_t st) {
+  const int N = pl->n_nodes, E = pl->n_edges;
+  const long long Rn = (long long)B * N, Re = (long long)B * E;
+  const int ldw1 = 2 * D + P + 1;
+  Arena sv(const_cast<float*>(saved), (size_t)-1);
+  // same layout as gmp_tc.cu's carve_nodes
+  const float* PsPd = sv.take<float>(Rn * 256);
+  const float* aggr = sv.take<float>(Rn * D);
+  const float* N1 = sv.take<float>(Rn * D);
+  const float* N2 = sv.take<float>(Rn * D);
+  const float* N3 = sv.take<float>(Rn * D);
+  const float* Yn = sv.take<float>(Rn * D);
+  Arena ar(ws, ws_bytes);
+  const long long re = Re > 0 ? Re : 1;
+  float* A0 = ar.take<float>(re * D);
+  float* A1 = ar.take<float>(re * D);
+  float* A2 = ar.take<float>(re * D);
+  float* Y = ar.take<float>(re * D);
+  float* Ge1 = ar.take<float>(re * D);
+  float* Ge2 = ar.take<float>(re * D);
+  float* Gn1 = ar.take<float>(Rn * D);
+  float* Gn2 = ar.take<float>(Rn * D);
+  float* g_aggr = ar.take<float>(Rn * D);
+  float* gPsPd = ar.take<float>(Rn * 256);
+  uint8_t* packs = ar.take<uint8_t>((size_t)10 * 65536);
+  if (!ar.ok()) {
+    set_error("bsms_gmp_backward: workspace too small for the tensor-core fp32-parity backward");
+    return BSMS_EWORKSPACE;
+  }
+  enum { kW2 = 0, kW3, kW4, kV2, kV3, kV4, kV1a, kV1b, kW1s, kW1d };
+  {
+    const float* Wp[10] = {w->w_edge[1], w->w_edge[2], w->w_edge[3], w->w_node[1], w->w_node[2], w->w_node[3],
+                           w->w_node[0], w->w_node[0] + D, w->w_edge[0] + (P + 1), w->w_edge[0] + (P + 1 + D)};
+    const int ld[10] = {D, D, D, D, D, D, 2 * D, 2 * D, ldw1, ldw1};
+    BSMS_TRY(pack_blocks_bf16split_ptrs(Wp, ld, 10, packs, st));
+  }
+  auto blk = [&](int i) { return (const uint8_t*)(packs + (size_t)i * 65536); };
+  auto lin1 = [&](const float* X, int ldx, int wi, int b_mn, const float* bias, int relu, const float* mask, const float* add,
+                  float* Yo, long long rows, int kind) {
+    const uint8_t* b[1] = {blk(wi)};
+    return lin_tc2_split(X, ldx, 1, b, b_mn, bias, relu, mask, D, add, D, nullptr, 0, Yo, D, nullptr, 0, rows, kind, st);
+  };
+  auto wg = [&](const float* G, int ldg, const float* X, int ldx, float* dW, int ldo, float* db, long long rows) {
+    const float* Gp[1] = {G};
+    const float* Xp[1] = {X};
+    float* dWp[1] = {dW};
+    float* dbp[1] = {db};
+    return wgrad_tc_split3(Gp, &ldg, Xp, &ldx, dWp, &ldo, dbp, 1, rows, st);
+  };
+  // ---- node MLP backward
+  BSMS_TRY(launch_ln_bwd_rows(Yn, g_out, D, Gn1, Rn, st));
+  BSMS_TRY(wg(Gn1, D, N3, D, gr->w_node[3], D, gr->b_node[3], Rn));
+  BSMS_TRY(lin1(Gn1, D, kV4, 1, nullptr, 0, N3, nullptr, Gn2, Rn, PK_DGRAD));
+  BSMS_TRY(wg(Gn2, D, N2, D, gr->w_node[2], D, gr->b_node[2], Rn));
+  BSMS_TRY(lin1(Gn2, D, kV3, 1, nullptr, 0, N2, nullptr, Gn1, Rn, PK_DGRAD));
+  BSMS_TRY(wg(Gn1, D, N1, D, gr->w_node[1], D, gr->b_node[1], Rn));
+  BSMS_TRY(lin1(Gn1, D, kV2, 1, nullptr, 0, N1, nullptr, Gn2, Rn, PK_DGRAD));  // Gn2 = gradient at the first node layer's output
+  {
+    const float* Gp[2] = {Gn2, Gn2};
+    const int ldg[2] = {D, D};
+    const float* Xp[2] = {x, aggr};
+    const int ldx[2] = {D, D};
+    float* dWp[2] = {gr->w_node[0], gr->w_node[0] + D};
+    const int ldo[2] = {2 * D, 2 * D};
+    float* dbp[2] = {gr->b_node[0], nullptr};
+    BSMS_TRY(wgrad_tc_split3(Gp, ldg, Xp, ldx, dWp, ldo, dbp, 2, Rn, st));
+    // [g_x | g_aggr] = Gn2 [V1a | V1b]; g_x also takes the residual path's g_out
+    const uint8_t* b[2] = {blk(kV1a), blk(kV1b)};
+    BSMS_TRY(lin_tc2_split(Gn2, D, 2, b, 1, nullptr, 0, nullptr, 0, g_out, D, nullptr, 0, g_x, D, g_aggr, D, Rn, PK_DGRAD, st));
+  }
+  // ---- edge MLP: recompute a0..a2, y; LayerNorm backward; three (weight gradient, data gradient) pairs
+  if (Re > 0) {
+    if (P == 1) BSMS_TRY(edge_combine<1>(PsPd, pos, pos_batched, pl, w->w_edge[0], nullptr, A0, B, st));
+    if (P == 2) BSMS_TRY(edge_combine<2>(PsPd, pos, pos_batched, pl, w->w_edge[0], nullptr, A0, B, st));
+    if (P == 3) BSMS_TRY(edge_combine<3>(PsPd, pos, pos_batched, pl, w->w_edge[0], nullptr, A0, B, st));
+    BSMS_TRY(lin1(A0, D, kW2, 0, w->b_edge[1], 1, nullptr, nullptr, A1, Re, PK_EDGE_FWD_GEMM));
+    BSMS_TRY(lin1(A1, D, kW3, 0, w->b_edge[2], 1, nullptr, nullptr, A2, Re, PK_EDGE_FWD_GEMM));
+    BSMS_TRY(lin1(A2, D, kW4, 0, w->b_edge[3], 0, nullptr, nullptr, Y, Re, PK_EDGE_FWD_GEMM));
+    {
+      ProfScope ps_(PK_LN_BWD, st);
+      k_ln_bwd<<<ceil_div(Re * 32, 256), 256, 0, st>>>(Y, g_aggr, D, pl->dst_d, E, N, Ge1, Re);
+    }
+    BSMS_LAUNCHED();
+    BSMS_TRY(wg(Ge1, D, A2, D, gr->w_edge[3], D, gr->b_edge[3], Re));
+    BSMS_TRY(lin1(Ge1, D, kW4, 1, nullptr, 0, A2, nullptr, Ge2, Re, PK_DGRAD));
+    BSMS_TRY(wg(Ge2, D, A1, D, gr->w_edge[2], D, gr->b_edge[2], Re));
+    BSMS_TRY(lin1(Ge2, D, kW3, 1, nullptr, 0, A1, nullptr, Ge1, Re, PK_DGRAD));
+    BSMS_TRY(wg(Ge1, D, A0, D, gr->w_edge[1], D, gr->b_edge[1], Re));
+    BSMS_TRY(lin1(Ge1, D, kW2, 1, nullptr, 0, A0, nullptr, Ge2, Re, PK_DGRAD));  // Ge2 = gradient at the edge input a0's pre-activation
+    if (P == 1) BSMS_TRY(fiber_wgrad<1>(Ge2, pos, pos_batched, pl, gr->w_edge[0], gr->b_edge[0], B, st));
+    if (P == 2) BSMS_TRY(fiber_wgrad<2>(Ge2, pos, pos_batched, pl, gr->w_edge[0], gr->b_edge[0], B, st));
+    if (P == 3) BSMS_TRY(fiber_wgrad<3>(Ge2, pos, pos_batched, pl, gr->w_edge[0], gr->b_edge[0], B, st));
+    {
+      ProfScope ps_(PK_EDGE_GRAD_SEGSUM, st);
+      k_edge_grad_segsum<<<ceil_div(Rn * 32, 256), 256, 0, st>>>(Ge2, pl->rowptr_d, pl->rowptr_s, pl->s2d, gPsPd, B, N, E);
+    }
+    BSMS_LAUNCHED();
+    // node-level gradients of the first edge layer: gW1s += gPs^T x, gW1d += gPd^T x, g_x += gPs W1s + gPd W1d
+    const float* Gp[2] = {gPsPd, gPsPd + 128};
+    const int ldg[2] = {256, 256};
+    const float* Xp[2] = {x, x};
+    const int ldx[2] = {D, D};
+    float* dWp[2] = {gr->w_edge[0] + (P + 1), gr->w_edge[0] + (P + 1 + D)};
+    const int ldo[2] = {ldw1, ldw1};
+    float* dbp[2] = {nullptr, nullptr};
+    BSMS_TRY(wgrad_tc_split3(Gp, ldg, Xp, ldx, dWp, ldo, dbp, 2, Rn, st));
+    BSMS_TRY(lin1(gPsPd, 256, kW1s, 1, nullptr, 0, nullptr, g_x, g_x, Rn, PK_DGRAD));
+    BSMS_TRY(lin1(gPsPd + 128, 256, kW1d, 1, nullptr, 0, nullptr, g_x, g_x, Rn, PK_DGRAD));
+  }
+  return BSMS_OK;
+}
+
 static int fp32_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos,
                         int pos_batched, int B, int P, const Fp32Acts& a, cudaStream_t st, int mode = BSMS_MODE_FP32,
                         uint8_t* wpack = nullptr) {
@@ -452,6 +587,11 @@ extern "C" int bsms_gmp_backward(const bsms_level_plan* pl, const bsms_gmp_weigh
   }
   if (mode == BSMS_MODE_BF16)
     return gmp_backward_tc(pl, w, x, pos, pos_batched, saved, g_out, g_x, gr, B, P, ws, ws_bytes, st);
+  // fp32-parity tensor-core mode with the forward's node-level intermediates at hand: every GEMM on tcgen05
+  // (BSMS_X3_BWD=ffma keeps the exact-fp32 FFMA backward below, which is also what runs without `saved`)
+  static const bool x3_tc = !(getenv("BSMS_X3_BWD") && strcmp(getenv("BSMS_X3_BWD"), "ffma") == 0);
+  if (mode == BSMS_MODE_FP16X3 && saved && x3_tc)
+    return backward_x3(pl, w, x, pos, pos_batched, saved, g_out, g_x, gr, B, P, ws, ws_bytes, st);
   const int N = pl->n_nodes, E = pl->n_edges;
   const long long Rn = (long long)B * N, Re = (long long)B * E;
   const int ldw1 = 2 * D + P + 1;

@@ -200,8 +200,14 @@ struct Lin2Params {
   int ntiles;
 };
 
-__global__ void __launch_bounds__(256, 2) k_lin2(const Lin2Params p) {
+// SPLIT = 0: bf16 operands (one MMA per K step).  SPLIT = 1: both operands as a two-way bf16 split (hi + lo, no scaling,
+// 16 significant bits, fp32's exponent range — what gradients need), three MMAs per K step (hi.hi + lo.hi + hi.lo); weight
+// blocks are [hi | lo] pairs (k_pack_weights<3>), KB must be 1 (a K = 256 layer is two launches, the second adding the first).
+template <int SPLIT>
+__global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_lin2(const Lin2Params p) {
   extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t NSP = SPLIT ? 2 : 1;
+  constexpr uint32_t WB = NSP * kWBlk;  // bytes of one packed weight block
   const uint32_t idesc = make_idesc(1, 128, 128, 0, p.b_mn ? 1u : 0u);
   const uint32_t s0 = smem_u32(smem_raw);
   const uint32_t sbase = (s0 + 1023u) & ~1023u;
@@ -211,7 +217,7 @@ __global__ void __launch_bounds__(256, 2) k_lin2(const Lin2Params p) {
   uint8_t* s_A = sp;
   float* s_stage = reinterpret_cast<float*>(sp);
   const uint32_t a_addr = sbase, w_addr = sbase + 2 * kWBlk;
-  float* s_bias = reinterpret_cast<float*>(sp + 2 * kWBlk + nblk * kWBlk);
+  float* s_bias = reinterpret_cast<float*>(sp + 2 * kWBlk + nblk * WB);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 256);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
   const int tid = threadIdx.x, warp = (int)uniform(threadIdx.x >> 5), lane = tid & 31;
@@ -229,10 +235,10 @@ __global__ void __launch_bounds__(256, 2) k_lin2(const Lin2Params p) {
   fence_after_sync();
   const uint32_t tmem_base = uniform(*s_tmem);
   if (tid == 0) {
-    mbar_expect_tx(bar_w, nblk * kWBlk);
+    mbar_expect_tx(bar_w, nblk * WB);
     for (int nb = 0; nb < p.NB; ++nb)
       for (int kb = 0; kb < p.KB; ++kb)
-        bulk_g2s(w_addr + (nb * p.KB + kb) * kWBlk, p.wblk[nb * 2 + kb], kWBlk, bar_w);
+        bulk_g2s(w_addr + (nb * p.KB + kb) * WB, p.wblk[nb * 2 + kb], WB, bar_w);
   }
   const int q = warp & 3, h = warp >> 2, r = q * 32 + lane;
   const uint32_t lane_off = (uint32_t)(q * 32) << 16;
@@ -243,8 +249,11 @@ __global__ void __launch_bounds__(256, 2) k_lin2(const Lin2Params p) {
 
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const long long row0 = (long long)tile * 128;
-    coop_rows_store<16>(s_A, warp * 16, lane, pre);
-    if (p.KB == 2) {
+    if (SPLIT)
+      coop_rows_store_split<16>(s_A, s_A + kWBlk, warp * 16, lane, pre);  // A hi | A lo (KB == 1)
+    else
+      coop_rows_store<16>(s_A, warp * 16, lane, pre);
+    if (!SPLIT && p.KB == 2) {
       float4 v1[16];
       coop_rows_load<16>(p.X[1], p.ldx[1], row0, p.rows, warp * 16, lane, v1);
       coop_rows_store<16>(s_A + kWBlk, warp * 16, lane, v1);
@@ -261,23 +270,36 @@ __global__ void __launch_bounds__(256, 2) k_lin2(const Lin2Params p) {
       // the loops run in warp-uniform control flow (whole warp), only the MMAs sit under the elected lane
       for (int nb = 0; nb < p.NB; ++nb)
         for (int kb = 0; kb < p.KB; ++kb) {
-          const uint32_t wb = w_addr + (nb * p.KB + kb) * kWBlk;
+          const uint32_t wb = w_addr + (nb * p.KB + kb) * WB;
           const uint32_t ab = a_addr + kb * kWBlk;
           const uint32_t dt = tmem_base + nb * 128;
           const uint32_t acc0 = kb > 0 ? 1u : 0u;
           if (p.b_mn) {
             if (elect_one()) {
 #pragma unroll
-              for (int ks = 0; ks < 8; ++ks)
-                mma_ss(dt, smem_desc_sw128(ab + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                       smem_desc_sw128(wb + ks * 2048, 16384, 1024), idesc, ks > 0 ? 1u : acc0);
+              for (int ks = 0; ks < 8; ++ks) {
+                const uint64_t ad = smem_desc_sw128(ab + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
+                const uint64_t bd = smem_desc_sw128(wb + ks * 2048, 16384, 1024);
+                mma_ss(dt, ad, bd, idesc, ks > 0 ? 1u : acc0);
+                if (SPLIT) {
+                  mma_ss(dt, smem_desc_sw128(ab + kWBlk + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024), bd, idesc, 1u);  // lo . hi
+                  mma_ss(dt, ad, smem_desc_sw128(wb + kWBlk + ks * 2048, 16384, 1024), idesc, 1u);                      // hi . lo
+                }
+              }
             }
           } else {
             if (elect_one()) {
 #pragma unroll
-              for (int ks = 0; ks < 8; ++ks)
-                mma_ss(dt, smem_desc_sw128(ab + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                       smem_desc_sw128(wb + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024), idesc, ks > 0 ? 1u : acc0);
+              for (int ks = 0; ks < 8; ++ks) {
+                const uint32_t ko = (ks >> 2) * 16384 + (ks & 3) * 32;
+                const uint64_t ad = smem_desc_sw128(ab + ko, 16, 1024);
+                const uint64_t bd = smem_desc_sw128(wb + ko, 16, 1024);
+                mma_ss(dt, ad, bd, idesc, ks > 0 ? 1u : acc0);
+                if (SPLIT) {
+                  mma_ss(dt, smem_desc_sw128(ab + kWBlk + ko, 16, 1024), bd, idesc, 1u);
+                  mma_ss(dt, ad, smem_desc_sw128(wb + kWBlk + ko, 16, 1024), idesc, 1u);
+                }
+              }
             }
           }
           __syncwarp();
@@ -566,9 +588,189 @@ int lin_tc2(const float* X0, int ldx0, const float* X1, int ldx1, int KB, int NB
   const int per_sm = nblk == 1 ? 2 : 1;
   const int grid = std::min(per_sm * sm_count(), p.ntiles);
   const size_t smem = 1024 + (2 + nblk) * kWBlk + 1024 + 64;
-  BSMS_CUDA(cudaFuncSetAttribute(k_lin2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 + 4 * kWBlk + 1024 + 64)));
+  BSMS_CUDA(cudaFuncSetAttribute(k_lin2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 + 4 * kWBlk + 1024 + 64)));
   ProfScope ps_(kind, st);
-  k_lin2<<<grid, 256, smem, st>>>(p);
+  k_lin2<0><<<grid, 256, smem, st>>>(p);
+  BSMS_LAUNCHED();
+  return BSMS_OK;
+}
+
+// The same layer in the two-way bf16 split arithmetic (16 significant bits per operand, three MMAs per K step): the
+// tensor-core form of the fp32-parity mode's backward GEMMs.  blocks: [hi | lo] pairs from pack_blocks_bf16split;
+// K = 128 only (NB = 1 or 2).
+int lin_tc2_split(const float* X0, int ldx0, int NB, const uint8_t* const* blocks, int b_mn, const float* bias, int relu,
+                  const float* mask, int ldmask, const float* add0, int ldadd0, const float* add1, int ldadd1, float* Y0,
+                  int ldy0, float* Y1, int ldy1, long long rows, int kind, cudaStream_t st) {
+  if (rows == 0) return BSMS_OK;
+  Lin2Params p;
+  p.X[0] = X0; p.X[1] = nullptr;
+  p.ldx[0] = ldx0; p.ldx[1] = 0;
+  p.KB = 1; p.NB = NB;
+  for (int i = 0; i < 4; ++i) p.wblk[i] = nullptr;
+  for (int nb = 0; nb < NB; ++nb) p.wblk[nb * 2] = blocks[nb];
+  p.b_mn = b_mn;
+  p.bias = bias;
+  p.relu = relu;
+  p.mask = mask;
+  p.ldmask = ldmask;
+  p.add[0] = add0; p.add[1] = add1;
+  p.ldadd[0] = ldadd0; p.ldadd[1] = ldadd1;
+  p.Y[0] = Y0; p.Y[1] = Y1;
+  p.ldy[0] = ldy0; p.ldy[1] = ldy1;
+  p.ln_out = nullptr;
+  p.res0 = p.res1 = nullptr;
+  p.rows = rows;
+  p.ntiles = ceil_div(rows, 128);
+  const int grid = std::min(sm_count(), p.ntiles);
+  const size_t smem = 1024 + (2 + 2 * NB) * kWBlk + 1024 + 64;  // A hi | A lo (= the fp32 staging), NB x [W hi | W lo]
+  BSMS_CUDA(cudaFuncSetAttribute(k_lin2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 + 6 * kWBlk + 1024 + 64)));
+  ProfScope ps_(kind, st);
+  k_lin2<1><<<grid, 256, smem, st>>>(p);
+  BSMS_LAUNCHED();
+  return BSMS_OK;
+}
+
+// fp32 [128,128] blocks -> [hi | lo] bf16 operand-image pairs (64 KB per block)
+int pack_blocks_bf16split(const PackList& pl, uint8_t* out, cudaStream_t st) {
+  ProfScope ps_(PK_OTHER, st);
+  k_pack_weights<3><<<pl.n, 256, 0, st>>>(pl, out);
+  BSMS_LAUNCHED();
+  return BSMS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// dW[128,128] += G^T X over all rows with BOTH operands as two-way bf16 splits (three MMAs per K step): the
+// weight gradient of the fp32-parity mode on tensor cores.  One 128 KB stage (G hi, G lo, X hi, X lo); the bias
+// gradient is the exact fp32 column sum of the rows as they pass through the registers.
+__global__ void __launch_bounds__(256, 1) k_wgrad_tc_split(const WgradBatch batch) {
+  extern __shared__ uint8_t smem_raw[];
+  const int cpp = batch.ctas_per_prob;
+  const WgradParams p = batch.prob[blockIdx.x / cpp];
+  const int cta_in_prob = blockIdx.x % cpp;
+  constexpr uint32_t IDESC_MM = make_idesc(1, 128, 128, 1, 1);
+  const uint32_t s0 = smem_u32(smem_raw);
+  const uint32_t sbase = (s0 + 1023u) & ~1023u;
+  uint8_t* sp = smem_raw + (sbase - s0);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(sp + 4 * kWBlk);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
+  const int tid = threadIdx.x, warp = (int)uniform(threadIdx.x >> 5), lane = tid & 31;
+  const uint32_t bar0 = smem_u32(&s_bar[0]);
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(s_tmem), 128);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = uniform(*s_tmem);
+  uint8_t *t_gh = sp, *t_gl = sp + kWBlk, *t_xh = sp + 2 * kWBlk, *t_xl = sp + 3 * kWBlk;
+  float4 acc_b = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t ph = 0;
+  int it = 0;
+  for (int tile = cta_in_prob; tile < p.ntiles; tile += cpp, ++it) {
+    const long long row0 = (long long)tile * 128;
+    // the rows of this tile travel to registers while the previous tile's MMAs still read the stage
+    float4 vg[8], vx[8];
+    coop_rows_load<8>(p.G, p.ldg, row0, p.rows, warp * 16, lane, vg);
+    coop_rows_load<8>(p.X, p.ldx, row0, p.rows, warp * 16, lane, vx);
+    if (it > 0) {
+      mbar_wait(bar0, ph);
+      ph ^= 1;
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      if (half == 1) {
+        coop_rows_load<8>(p.G, p.ldg, row0, p.rows, warp * 16 + 8, lane, vg);
+        coop_rows_load<8>(p.X, p.ldx, row0, p.rows, warp * 16 + 8, lane, vx);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        acc_b.x += vg[u].x; acc_b.y += vg[u].y; acc_b.z += vg[u].z; acc_b.w += vg[u].w;
+      }
+      coop_rows_store_split<8>(t_gh, t_gl, warp * 16 + 8 * half, lane, vg);
+      coop_rows_store_split<8>(t_xh, t_xl, warp * 16 + 8 * half, lane, vx);
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) {
+      fence_after_sync();
+      if (elect_one()) {
+        const uint32_t gh = sbase, gl = sbase + kWBlk, xh = sbase + 2 * kWBlk, xl = sbase + 3 * kWBlk;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t dgh = smem_desc_sw128(gh + ks * 2048, 16384, 1024), dgl = smem_desc_sw128(gl + ks * 2048, 16384, 1024);
+          const uint64_t dxh = smem_desc_sw128(xh + ks * 2048, 16384, 1024), dxl = smem_desc_sw128(xl + ks * 2048, 16384, 1024);
+          mma_ss(tmem_base, dgh, dxh, IDESC_MM, (it > 0 || ks > 0) ? 1u : 0u);
+          mma_ss(tmem_base, dgl, dxh, IDESC_MM, 1u);
+          mma_ss(tmem_base, dgh, dxl, IDESC_MM, 1u);
+        }
+        mma_commit(bar0);
+      }
+      __syncwarp();
+    }
+  }
+  if (it > 0) {
+    mbar_wait(bar0, ph);
+    fence_after_sync();
+    const int q = warp & 3, hh = warp >> 2;  // TMEM lane = output channel n
+    const int n = q * 32 + lane;
+    uint32_t r0[32], r1[32];
+    const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + 64 * hh;
+    tmem_ld32(ta, r0);
+    tmem_ld32(ta + 32, r1);
+    wait_ld();
+    float* dst = p.dW + (size_t)n * p.ldo + 64 * hh;
+#pragma unroll
+    for (int t = 0; t < 32; ++t) atomicAdd(dst + t, __uint_as_float(r0[t]));
+#pragma unroll
+    for (int t = 0; t < 32; ++t) atomicAdd(dst + 32 + t, __uint_as_float(r1[t]));
+    if (p.db) {
+      atomicAdd(p.db + 4 * lane + 0, acc_b.x);
+      atomicAdd(p.db + 4 * lane + 1, acc_b.y);
+      atomicAdd(p.db + 4 * lane + 2, acc_b.z);
+      atomicAdd(p.db + 4 * lane + 3, acc_b.w);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+WgradParams wgrad_problem(const float* G, int ldg, const float* X, int ldx, float* dW, int ldo, float* db, long long rows);
+// plain-pointer front ends for gmp.cu (which does not see the packed-operand headers)
+int pack_blocks_bf16split_ptrs(const float* const* W, const int* ld, int n, uint8_t* out, cudaStream_t st) {
+  PackList pl;
+  pl.n = n;
+  for (int i = 0; i < n; ++i) {
+    pl.w[i] = W[i];
+    pl.ld[i] = ld[i];
+  }
+  return pack_blocks_bf16split(pl, out, st);
+}
+int wgrad_tc_split_batch(const WgradParams* probs, int nprob, cudaStream_t st);
+int wgrad_tc_split3(const float* const* G, const int* ldg, const float* const* X, const int* ldx, float* const* dW, const int* ldo,
+                    float* const* db, int nprob, long long rows, cudaStream_t st) {
+  WgradParams pr[6];
+  for (int i = 0; i < nprob; ++i) pr[i] = wgrad_problem(G[i], ldg[i], X[i], ldx[i], dW[i], ldo[i], db[i], rows);
+  return wgrad_tc_split_batch(pr, nprob, st);
+}
+
+int wgrad_tc_split_batch(const WgradParams* probs, int nprob, cudaStream_t st) {
+  if (nprob == 0 || probs[0].rows == 0) return BSMS_OK;
+  WgradBatch b;
+  b.nprob = nprob;
+  const int ntiles = ceil_div(probs[0].rows, 128);
+  for (int i = 0; i < nprob; ++i) {
+    b.prob[i] = probs[i];
+    b.prob[i].ntiles = ntiles;
+  }
+  b.ctas_per_prob = std::max(1, std::min(ntiles, sm_count() / nprob));
+  const size_t smem = 1024 + 4 * kWBlk + 64;
+  BSMS_CUDA(cudaFuncSetAttribute(k_wgrad_tc_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope ps_(PK_WGRAD, st);
+  k_wgrad_tc_split<<<b.ctas_per_prob * nprob, 256, smem, st>>>(b);
   BSMS_LAUNCHED();
   return BSMS_OK;
 }

@@ -102,7 +102,7 @@ class _GMPFunction(torch.autograd.Function):
         w = _weights_struct(params)
         # node-level intermediates kept for backward (fused tcgen05 modes; nothing per-edge is kept)
         saved = None
-        if mode == _lib.MODE_BF16 and any(ctx.needs_input_grad):
+        if mode in (_lib.MODE_BF16, _lib.MODE_FP16X3) and any(ctx.needs_input_grad):
             saved = torch.empty(int(lib.bsms_gmp_saved_bytes(B, N)), dtype=torch.uint8, device=x3.device)
         with torch.cuda.device(x3.device):
             check(lib.bsms_gmp_forward_packed(level.byref(), C.byref(w), ptr(packed), ptr(x3), ptr(pos), pos_batched, ptr(skip3),

@@ -179,3 +179,32 @@ def test_bsgmp_bf16_benchmark_configuration_fwd_bwd(dev):
     assert e_emu < 5e-3
     assert e_gh < 2e-2
     assert errs[worst] < 2e-2, (worst, errs[worst])
+
+
+@pytest.mark.parametrize("case,hname", [("grid12_b3", "grid12"), ("ico3", "ico3"), ("grid44", "grid44"), ("grid72", "grid72"),
+                                        ("grid72d7", "grid72d7")])
+def test_bsgmp_fp16x3_tensor_core_backward_against_reference_golden(dev, case, hname):
+    """The default (fp32-parity) mode end to end on tensor cores: forward on the fp16-split tcgen05 kernels, backward with
+    every GEMM as a two-way bf16-split tcgen05 GEMM (gmp.cu backward_x3).  Same tolerances as the exact-fp32 mode:
+    forward 1e-5, gradients 5e-4 against the goldens of the unmodified reference."""
+    rec = load_npz(f"bsgmp_{case}.npz")
+    if "grad_h" not in rec.files:
+        pytest.skip("golden without gradients")
+    m_gs, m_ids, pos, d = load_hier(hname)
+    h, ps = bsgmp_inputs(rec, pos, pos.shape[0])
+    model = build(d, int(rec["P"]), int(rec["seed"]), dev, mode="fp16x3")
+    hg = h.to(dev).requires_grad_(True)
+    out = model(hg, [i.to(dev) for i in m_ids], [g.to(dev) for g in m_gs], ps.to(dev))
+    rs = int(rec["row_stride"])
+    assert max_rel(out.detach().cpu()[..., ::rs, :], rec["out"]) < FWD_TOL
+    out.square().mean().backward()
+    e_h = max_rel(hg.grad.cpu()[..., ::rs, :], rec["grad_h"])
+    sd = dict(model.named_parameters())
+    errs = {k[5:]: max_rel(sd[k[5:]].grad.cpu(), rec[k]) for k in rec.files if k.startswith("grad:")}
+    worst = max(errs, key=errs.get) if errs else None
+    print(f"\n[fp16x3 tc-bwd {case}] grad_h {e_h:.2e}; worst of {len(errs)} parameter gradients {errs.get(worst, 0):.2e} ({worst})")
+    assert e_h < GRAD_TOL
+    for k, v in errs.items():
+        assert v < GRAD_TOL, (k, v)
+    norms = np.array([float(v.grad.double().norm()) for _, v in sorted(sd.items())])
+    assert np.allclose(norms, rec["grad_norms"], rtol=2e-4)
