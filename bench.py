@@ -749,6 +749,11 @@ def main():
             tj = traffic_db.get(r["kernel"]) if r else None
             if tj:
                 r["traffic"] = tj["dram_bytes_per_launch"]
+                rows_l = tj["edge_rows_in_launch"]
+                per_row = byts[r["kernel"]] / Re  # includes the node-row share
+                r["traffic_launch"] = {"edge_rows": rows_l, "algorithmic_bytes": per_row * rows_l,
+                                       "dram_over_algorithmic": tj["dram_bytes_per_launch"] / (per_row * rows_l),
+                                       "captured_at_commit": traffic_db.get("_captured_at_commit")}
                 r["traffic_note"] = tj["note"]
 
         add_traffic(roofline)
@@ -823,6 +828,43 @@ def main():
                            "gpu_launches_per_step": mr["launches_per_step"],
                            "n1_reference": "the same mesh un-partitioned on rank 0's GPU, eager, CUDA events, same run"}
 
+    # ---- N = 1: the same step in the fp32-PARITY mode (fp16x3: forward within 1e-5 of the reference, gradients 5e-4;
+    #      every GEMM of forward and backward on tcgen05 with split operands), next to the bf16 headline
+    parity_mode = None
+    if world == 1 and args.mode != "fp16x3" and os.environ.get("BSMS_BENCH_PARITY_MODE", "1") != "0":
+        from tests.util import max_rel
+        model_p = BSGMP(args.depth, D, 3, 2, mode="fp16x3").to(dev)
+        model_p.load_state_dict(O.init_params(args.depth, pos_dim=2, seed=0))
+        params_p = list(model_p.parameters())
+
+        def step_p():
+            for q in params_p:
+                q.grad = None
+            h_dev.grad = None
+            model_p(h_dev, ids, gs, pos_dev).square().mean().backward()
+
+        for _ in range(3):
+            step_p()
+        torch.cuda.synchronize()
+        ep0, ep1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ep0.record()
+        for _ in range(5):
+            step_p()
+        ep1.record()
+        torch.cuda.synchronize()
+        ms_p = ep0.elapsed_time(ep1) / 5
+        with torch.no_grad():
+            out_p = model_p(h_dev[:1], ids, gs, pos_dev[:1]).cpu()
+            ref_p = O.bsgmp(h_host[:1].double(), [torch.from_numpy(i) for i in m_ids], [torch.from_numpy(g) for g in m_gs],
+                            pos_host[:1].double(), {k: v.double() for k, v in O.init_params(args.depth, pos_dim=2, seed=0).items()},
+                            args.depth)
+        parity_mode = {"mode": "fp16x3", "ms_per_step": ms_p, "value": B * E0 / (ms_p * 1e-3) / 1e6, "unit": "M-edges/s",
+                       "fwd_max_rel": max_rel(out_p, ref_p), "fwd_tol": 1e-5, "steps": 5, "warmup": 3,
+                       "note": "same workload, forward and backward GEMMs on tcgen05 with two-way split operands (3 MMAs per K step)"}
+        assert parity_mode["fwd_max_rel"] < 1e-5, parity_mode
+        del model_p, params_p
+        torch.cuda.empty_cache()
+
     # ---- N = 1: BASELINE.json configs 2 and 4 (whole-model rollouts, B = 1) in the same run, short form
     rollouts = None
     if world == 1 and os.environ.get("BSMS_BENCH_ROLLOUT", "1") != "0":
@@ -852,10 +894,13 @@ def main():
             "clocks": {"sm_mhz": clk.get("sm_mhz"), "sm_max_mhz": clk.get("sm_max_mhz"), "reasons": clk.get("reasons")},
             "e2e": {"value": world * B * E0 / e2e_s / 1e6, "unit": "M-edges/s",
                     "h2d_bytes_per_step": int(h_host.numel() * 4 + pos_host.numel() * 4), "d2h_bytes_per_step": 4,
-                    "ms_per_step": e2e_s * 1e3},
+                    "ms_per_step": e2e_s * 1e3,
+                    "note": "every step uploads its features and positions from pinned host memory (double-buffered on a copy "
+                            "stream) and reads back its 4-byte loss; outputs and gradients of a training step stay on the device "
+                            "(the rollout configs in extra.rollouts return every state to the host)"},
             "gpu_launches": int(launches),
             "roofline": roofline, "roofline_fused_edge_kernel": roofline_edge, "kernel_breakdown": breakdown, "cpu_baseline": cpu,
-            "self_check": self_check, "extra": {"mesh_strong": mesh_strong, "rollouts": rollouts},
+            "self_check": self_check, "extra": {"mesh_strong": mesh_strong, "rollouts": rollouts, "parity_mode": parity_mode},
         }
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -134,21 +134,25 @@ __device__ __forceinline__ void coop_rows_store(uint8_t* tile, int r_begin, int 
   }
 }
 
-// the same rows as a two-way bf16 split: hi = bf16(v) -> tile_hi, lo = bf16(v - hi) -> tile_lo
+// the same rows as a two-way fp16 split of v * scale: hi = fp16(v s) -> tile_hi, lo = fp16(v s - hi) -> tile_lo (22
+// significant bits; s is a power of two; values are clamped to the fp16 range so an outlier saturates instead of
+// becoming infinite)
 template <int NR>
-__device__ __forceinline__ void coop_rows_store_split(uint8_t* tile_hi, uint8_t* tile_lo, int r_begin, int lane, const float4 (&v)[NR]) {
+__device__ __forceinline__ void coop_rows_store_split(uint8_t* tile_hi, uint8_t* tile_lo, int r_begin, int lane, const float4 (&v)[NR],
+                                                      float scale) {
   const uint32_t col_off = (uint32_t)((lane >> 4) * 16384 + (lane & 1) * 8);
   const int chunk7 = (lane >> 1) & 7;
+  auto cl = [](float x) { return fminf(fmaxf(x, -65000.f), 65000.f); };
 #pragma unroll
   for (int u = 0; u < NR; ++u) {
     const int r = r_begin + u;
-    const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[u].x, v[u].y), h1 = __floats2bfloat162_rn(v[u].z, v[u].w);
-    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    const float s0 = cl(v[u].x * scale), s1 = cl(v[u].y * scale), s2 = cl(v[u].z * scale), s3 = cl(v[u].w * scale);
+    const __half h0 = __float2half_rn(s0), h1 = __float2half_rn(s1), h2 = __float2half_rn(s2), h3 = __float2half_rn(s3);
     uint2 ph, pl;
-    ph.x = *reinterpret_cast<const uint32_t*>(&h0);
-    ph.y = *reinterpret_cast<const uint32_t*>(&h1);
-    pl.x = pack_bf16(v[u].x - f0.x, v[u].y - f0.y);
-    pl.y = pack_bf16(v[u].z - f1.x, v[u].w - f1.y);
+    ph.x = pack_f16(h0, h1);
+    ph.y = pack_f16(h2, h3);
+    pl.x = pack_f16(__float2half_rn(s0 - __half2float(h0)), __float2half_rn(s1 - __half2float(h1)));
+    pl.y = pack_f16(__float2half_rn(s2 - __half2float(h2)), __float2half_rn(s3 - __half2float(h3)));
     const uint32_t off = col_off + r * 128 + ((chunk7 ^ (r & 7)) << 4);
     *reinterpret_cast<uint2*>(tile_hi + off) = ph;
     *reinterpret_cast<uint2*>(tile_lo + off) = pl;
@@ -167,18 +171,13 @@ __global__ void k_pack_weights(PackList pl, uint8_t* __restrict__ out) {
   const int blk = blockIdx.x;
   const float* W = pl.w[blk];
   const int ld = pl.ld[blk];
-  uint8_t* o = out + (size_t)blk * (NSPLIT == 1 ? 1 : 2) * kWBlk;
+  uint8_t* o = out + (size_t)blk * NSPLIT * kWBlk;
   for (int idx = threadIdx.x; idx < 128 * 128; idx += blockDim.x) {
     int n = idx >> 7, k = idx & 127;
     float v = W[(size_t)n * ld + k];
     uint32_t off = wblk_offset(n, k);
     if (NSPLIT == 1) {
       *reinterpret_cast<__nv_bfloat16*>(o + off) = __float2bfloat16_rn(v);
-    } else if (NSPLIT == 3) {
-      // two-way bf16 split, no scaling (bf16 has fp32's exponent range): 16 significant bits, for the gradient GEMMs
-      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-      *reinterpret_cast<__nv_bfloat16*>(o + off) = hi;
-      *reinterpret_cast<__nv_bfloat16*>(o + kWBlk + off) = __float2bfloat16_rn(v - __bfloat162float(hi));
     } else {
       float s = v * kWScale;
       __half hi = __float2half_rn(s);

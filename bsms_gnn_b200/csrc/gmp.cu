@@ -291,16 +291,19 @@ struct PackList;
 struct WgradParams;
 int lin_tc2_split(const float* X0, int ldx0, int NB, const uint8_t* const* blocks, int b_mn, const float* bias, int relu,
                   const float* mask, int ldmask, const float* add0, int ldadd0, const float* add1, int ldadd1, float* Y0,
-                  int ldy0, float* Y1, int ldy1, long long rows, int kind, cudaStream_t st);
-int pack_blocks_bf16split_ptrs(const float* const* W, const int* ld, int n, uint8_t* out, cudaStream_t st);
+                  int ldy0, float* Y1, int ldy1, long long rows, int kind, const float* a_scale_dev, cudaStream_t st);
+int grad_scale_for(const float* g_out, long long n, float* scratch2, cudaStream_t st);
 int wgrad_tc_split3(const float* const* G, const int* ldg, const float* const* X, const int* ldx, float* const* dW, const int* ldo,
-                    float* const* db, int nprob, long long rows, cudaStream_t st);
+                    float* const* db, int nprob, long long rows, const float* g_scale_dev, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------------------------
 // Backward of the fp32-parity tensor-core mode (BSMS_MODE_FP16X3) ON TENSOR CORES.  Every GEMM of the backward — the
-// recomputation of the three edge layers, the six data gradients and the eleven weight gradients — runs as tcgen05
-// MMAs over two-way bf16 splits of both operands (16 significant bits, fp32's exponent range: gradients of any
-// magnitude; three MMAs per K step), with fp32 accumulation and fp32 tensors in HBM.  Per-edge activations are
+// recomputation of the three edge layers, the data gradients and the weight gradients — runs as tcgen05 MMAs over
+// two-way fp16 splits of both operands (22 significant bits, three MMAs per K step; a two-way bf16 split, 16 bits, was
+// measured first and missed the 5e-4 gradient bar: 1.4e-3), with fp32 accumulation and fp32 tensors in HBM.  Operands are
+// scaled by powers of two so that the fp16 pieces stay normal: weights by 2^8 and activations by 2^4 as in the forward
+// (whose packed weight images are reused from `saved`), gradients by ONE device-resident scale per call derived from
+// max|g_out| (their magnitude follows the caller's loss scaling).  Per-edge activations are
 // recomputed into the workspace (never kept between forward and backward); the node-level tensors come from
 // `saved`.  Non-GEMM kernels (gather/combine, LayerNorm backward, segment sums) are the exact-fp32 ones of the
 // fp32 mode.  Reference: src/ops/basic.py:48-98 differentiated by autograd.
@@ -330,30 +333,31 @@ static int backward_x3(const bsms_level_plan* pl, const bsms_gmp_weights* w, con
   float* Gn2 = ar.take<float>(Rn * D);
   float* g_aggr = ar.take<float>(Rn * D);
   float* gPsPd = ar.take<float>(Rn * 256);
-  uint8_t* packs = ar.take<uint8_t>((size_t)10 * 65536);
+  float* gscale2 = ar.take<float>(2);  // [amax bits, scale]
   if (!ar.ok()) {
     set_error("bsms_gmp_backward: workspace too small for the tensor-core fp32-parity backward");
     return BSMS_EWORKSPACE;
   }
-  enum { kW2 = 0, kW3, kW4, kV2, kV3, kV4, kV1a, kV1b, kW1s, kW1d };
-  {
-    const float* Wp[10] = {w->w_edge[1], w->w_edge[2], w->w_edge[3], w->w_node[1], w->w_node[2], w->w_node[3],
-                           w->w_node[0], w->w_node[0] + D, w->w_edge[0] + (P + 1), w->w_edge[0] + (P + 1 + D)};
-    const int ld[10] = {D, D, D, D, D, D, 2 * D, 2 * D, ldw1, ldw1};
-    BSMS_TRY(pack_blocks_bf16split_ptrs(Wp, ld, 10, packs, st));
-  }
+  // the forward's fp16-split weight images ([hi | lo], 64 KB per block) sit behind the node tensors in `saved`, in the
+  // block order of gmp_tc.cu: W2, W3, W4, W1s, W1d, V1a, V1b, V2, V3, V4
+  const uint8_t* packs = reinterpret_cast<const uint8_t*>(sv.take<uint8_t>(1));
+  enum { kW2 = 0, kW3, kW4, kW1s, kW1d, kV1a, kV1b, kV2, kV3, kV4 };
+  BSMS_TRY(grad_scale_for(g_out, Rn * D, gscale2, st));
+  const float* gs = gscale2 + 1;
   auto blk = [&](int i) { return (const uint8_t*)(packs + (size_t)i * 65536); };
+  // act: the A operand is an activation (static scale); otherwise a gradient (device scale)
   auto lin1 = [&](const float* X, int ldx, int wi, int b_mn, const float* bias, int relu, const float* mask, const float* add,
-                  float* Yo, long long rows, int kind) {
+                  float* Yo, long long rows, int kind, bool act = false) {
     const uint8_t* b[1] = {blk(wi)};
-    return lin_tc2_split(X, ldx, 1, b, b_mn, bias, relu, mask, D, add, D, nullptr, 0, Yo, D, nullptr, 0, rows, kind, st);
+    return lin_tc2_split(X, ldx, 1, b, b_mn, bias, relu, mask, D, add, D, nullptr, 0, Yo, D, nullptr, 0, rows, kind,
+                         act ? nullptr : gs, st);
   };
   auto wg = [&](const float* G, int ldg, const float* X, int ldx, float* dW, int ldo, float* db, long long rows) {
     const float* Gp[1] = {G};
     const float* Xp[1] = {X};
     float* dWp[1] = {dW};
     float* dbp[1] = {db};
-    return wgrad_tc_split3(Gp, &ldg, Xp, &ldx, dWp, &ldo, dbp, 1, rows, st);
+    return wgrad_tc_split3(Gp, &ldg, Xp, &ldx, dWp, &ldo, dbp, 1, rows, gs, st);
   };
   // ---- node MLP backward
   BSMS_TRY(launch_ln_bwd_rows(Yn, g_out, D, Gn1, Rn, st));
@@ -371,19 +375,19 @@ static int backward_x3(const bsms_level_plan* pl, const bsms_gmp_weights* w, con
     float* dWp[2] = {gr->w_node[0], gr->w_node[0] + D};
     const int ldo[2] = {2 * D, 2 * D};
     float* dbp[2] = {gr->b_node[0], nullptr};
-    BSMS_TRY(wgrad_tc_split3(Gp, ldg, Xp, ldx, dWp, ldo, dbp, 2, Rn, st));
+    BSMS_TRY(wgrad_tc_split3(Gp, ldg, Xp, ldx, dWp, ldo, dbp, 2, Rn, gs, st));
     // [g_x | g_aggr] = Gn2 [V1a | V1b]; g_x also takes the residual path's g_out
     const uint8_t* b[2] = {blk(kV1a), blk(kV1b)};
-    BSMS_TRY(lin_tc2_split(Gn2, D, 2, b, 1, nullptr, 0, nullptr, 0, g_out, D, nullptr, 0, g_x, D, g_aggr, D, Rn, PK_DGRAD, st));
+    BSMS_TRY(lin_tc2_split(Gn2, D, 2, b, 1, nullptr, 0, nullptr, 0, g_out, D, nullptr, 0, g_x, D, g_aggr, D, Rn, PK_DGRAD, gs, st));
   }
   // ---- edge MLP: recompute a0..a2, y; LayerNorm backward; three (weight gradient, data gradient) pairs
   if (Re > 0) {
     if (P == 1) BSMS_TRY(edge_combine<1>(PsPd, pos, pos_batched, pl, w->w_edge[0], nullptr, A0, B, st));
     if (P == 2) BSMS_TRY(edge_combine<2>(PsPd, pos, pos_batched, pl, w->w_edge[0], nullptr, A0, B, st));
     if (P == 3) BSMS_TRY(edge_combine<3>(PsPd, pos, pos_batched, pl, w->w_edge[0], nullptr, A0, B, st));
-    BSMS_TRY(lin1(A0, D, kW2, 0, w->b_edge[1], 1, nullptr, nullptr, A1, Re, PK_EDGE_FWD_GEMM));
-    BSMS_TRY(lin1(A1, D, kW3, 0, w->b_edge[2], 1, nullptr, nullptr, A2, Re, PK_EDGE_FWD_GEMM));
-    BSMS_TRY(lin1(A2, D, kW4, 0, w->b_edge[3], 0, nullptr, nullptr, Y, Re, PK_EDGE_FWD_GEMM));
+    BSMS_TRY(lin1(A0, D, kW2, 0, w->b_edge[1], 1, nullptr, nullptr, A1, Re, PK_EDGE_FWD_GEMM, true));
+    BSMS_TRY(lin1(A1, D, kW3, 0, w->b_edge[2], 1, nullptr, nullptr, A2, Re, PK_EDGE_FWD_GEMM, true));
+    BSMS_TRY(lin1(A2, D, kW4, 0, w->b_edge[3], 0, nullptr, nullptr, Y, Re, PK_EDGE_FWD_GEMM, true));
     {
       ProfScope ps_(PK_LN_BWD, st);
       k_ln_bwd<<<ceil_div(Re * 32, 256), 256, 0, st>>>(Y, g_aggr, D, pl->dst_d, E, N, Ge1, Re);
@@ -411,7 +415,7 @@ static int backward_x3(const bsms_level_plan* pl, const bsms_gmp_weights* w, con
     float* dWp[2] = {gr->w_edge[0] + (P + 1), gr->w_edge[0] + (P + 1 + D)};
     const int ldo[2] = {ldw1, ldw1};
     float* dbp[2] = {nullptr, nullptr};
-    BSMS_TRY(wgrad_tc_split3(Gp, ldg, Xp, ldx, dWp, ldo, dbp, 2, Rn, st));
+    BSMS_TRY(wgrad_tc_split3(Gp, ldg, Xp, ldx, dWp, ldo, dbp, 2, Rn, gs, st));
     BSMS_TRY(lin1(gPsPd, 256, kW1s, 1, nullptr, 0, nullptr, g_x, g_x, Rn, PK_DGRAD));
     BSMS_TRY(lin1(gPsPd + 128, 256, kW1d, 1, nullptr, 0, nullptr, g_x, g_x, Rn, PK_DGRAD));
   }

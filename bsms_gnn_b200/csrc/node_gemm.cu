@@ -193,6 +193,8 @@ struct Lin2Params {
   int ldadd[2];
   float* Y[2];
   int ldy[2];
+  float a_scale;             // SPLIT: power-of-two scale of the A operand (activations: kActScale) ...
+  const float* a_scale_dev;  // ... or, when non-null, read from device memory (gradients: one scale per GMP backward)
   float* ln_out;  // NB == 1: ln_out = LN(y) + res0 (+ res1), rows of 128
   const float* res0;
   const float* res1;
@@ -200,15 +202,19 @@ struct Lin2Params {
   int ntiles;
 };
 
-// SPLIT = 0: bf16 operands (one MMA per K step).  SPLIT = 1: both operands as a two-way bf16 split (hi + lo, no scaling,
-// 16 significant bits, fp32's exponent range — what gradients need), three MMAs per K step (hi.hi + lo.hi + hi.lo); weight
-// blocks are [hi | lo] pairs (k_pack_weights<3>), KB must be 1 (a K = 256 layer is two launches, the second adding the first).
+// SPLIT = 0: bf16 operands (one MMA per K step).  SPLIT = 1: both operands as a two-way fp16 split of a power-of-two
+// scaled value (hi + lo, 22 significant bits), three MMAs per K step (hi.hi + lo.hi + hi.lo), the accumulator is scaled
+// back in the epilogue; weight blocks are the [hi | lo] pairs of k_pack_weights<2> (scale kWScale); the A scale is
+// kActScale for activations and a device-resident scale for gradients (whose magnitude follows the loss).  KB must be 1
+// (a K = 256 layer is two launches, the second adding the first).
 template <int SPLIT>
 __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_lin2(const Lin2Params p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t NSP = SPLIT ? 2 : 1;
   constexpr uint32_t WB = NSP * kWBlk;  // bytes of one packed weight block
-  const uint32_t idesc = make_idesc(1, 128, 128, 0, p.b_mn ? 1u : 0u);
+  const uint32_t idesc = make_idesc(SPLIT ? 0u : 1u, 128, 128, 0, p.b_mn ? 1u : 0u);
+  const float a_scale = SPLIT ? (p.a_scale_dev ? *p.a_scale_dev : p.a_scale) : 1.f;
+  const float out_scale = SPLIT ? 1.f / (a_scale * kWScale) : 1.f;
   const uint32_t s0 = smem_u32(smem_raw);
   const uint32_t sbase = (s0 + 1023u) & ~1023u;
   uint8_t* sp = smem_raw + (sbase - s0);
@@ -250,7 +256,7 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_lin2(const Lin2Params p)
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const long long row0 = (long long)tile * 128;
     if (SPLIT)
-      coop_rows_store_split<16>(s_A, s_A + kWBlk, warp * 16, lane, pre);  // A hi | A lo (KB == 1)
+      coop_rows_store_split<16>(s_A, s_A + kWBlk, warp * 16, lane, pre, a_scale);  // A hi | A lo (KB == 1)
     else
       coop_rows_store<16>(s_A, warp * 16, lane, pre);
     if (!SPLIT && p.KB == 2) {
@@ -326,7 +332,8 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_lin2(const Lin2Params p)
           float o[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float x = __uint_as_float(rr_[q4 * 4 + e]) + s_bias[nb * 128 + 64 * h + 32 * hh + q4 * 4 + e];
+            const float acc = SPLIT ? __uint_as_float(rr_[q4 * 4 + e]) * out_scale : __uint_as_float(rr_[q4 * 4 + e]);
+            const float x = acc + s_bias[nb * 128 + 64 * h + 32 * hh + q4 * 4 + e];
             o[e] = p.relu ? fmaxf(x, 0.f) : x;
           }
           const int c4 = 16 * h + 8 * hh + q4;
@@ -582,6 +589,8 @@ int lin_tc2(const float* X0, int ldx0, const float* X1, int ldx1, int KB, int NB
   p.ln_out = ln_out;
   p.res0 = res0;
   p.res1 = res1;
+  p.a_scale = 1.f;
+  p.a_scale_dev = nullptr;
   p.rows = rows;
   p.ntiles = ceil_div(rows, 128);
   const int nblk = KB * NB;
@@ -595,12 +604,13 @@ int lin_tc2(const float* X0, int ldx0, const float* X1, int ldx1, int KB, int NB
   return BSMS_OK;
 }
 
-// The same layer in the two-way bf16 split arithmetic (16 significant bits per operand, three MMAs per K step): the
-// tensor-core form of the fp32-parity mode's backward GEMMs.  blocks: [hi | lo] pairs from pack_blocks_bf16split;
+// The same layer in the two-way fp16 split arithmetic (22 significant bits per operand, three MMAs per K step): the
+// tensor-core form of the fp32-parity mode's backward GEMMs.  blocks: the [hi | lo] pairs the forward packed
+// (k_pack_weights<2>); a_scale_dev (device, power of two) scales a gradient operand, null = activations (kActScale);
 // K = 128 only (NB = 1 or 2).
 int lin_tc2_split(const float* X0, int ldx0, int NB, const uint8_t* const* blocks, int b_mn, const float* bias, int relu,
                   const float* mask, int ldmask, const float* add0, int ldadd0, const float* add1, int ldadd1, float* Y0,
-                  int ldy0, float* Y1, int ldy1, long long rows, int kind, cudaStream_t st) {
+                  int ldy0, float* Y1, int ldy1, long long rows, int kind, const float* a_scale_dev, cudaStream_t st) {
   if (rows == 0) return BSMS_OK;
   Lin2Params p;
   p.X[0] = X0; p.X[1] = nullptr;
@@ -619,6 +629,8 @@ int lin_tc2_split(const float* X0, int ldx0, int NB, const uint8_t* const* block
   p.ldy[0] = ldy0; p.ldy[1] = ldy1;
   p.ln_out = nullptr;
   p.res0 = p.res1 = nullptr;
+  p.a_scale = kActScale;
+  p.a_scale_dev = a_scale_dev;
   p.rows = rows;
   p.ntiles = ceil_div(rows, 128);
   const int grid = std::min(sm_count(), p.ntiles);
@@ -630,24 +642,19 @@ int lin_tc2_split(const float* X0, int ldx0, int NB, const uint8_t* const* block
   return BSMS_OK;
 }
 
-// fp32 [128,128] blocks -> [hi | lo] bf16 operand-image pairs (64 KB per block)
-int pack_blocks_bf16split(const PackList& pl, uint8_t* out, cudaStream_t st) {
-  ProfScope ps_(PK_OTHER, st);
-  k_pack_weights<3><<<pl.n, 256, 0, st>>>(pl, out);
-  BSMS_LAUNCHED();
-  return BSMS_OK;
-}
-
 // ------------------------------------------------------------------------------------------
-// dW[128,128] += G^T X over all rows with BOTH operands as two-way bf16 splits (three MMAs per K step): the
-// weight gradient of the fp32-parity mode on tensor cores.  One 128 KB stage (G hi, G lo, X hi, X lo); the bias
-// gradient is the exact fp32 column sum of the rows as they pass through the registers.
-__global__ void __launch_bounds__(256, 1) k_wgrad_tc_split(const WgradBatch batch) {
+// dW[128,128] += G^T X over all rows with BOTH operands as two-way fp16 splits of scaled values (three MMAs per K
+// step, 22 significant bits): the weight gradient of the fp32-parity mode on tensor cores.  One 128 KB stage (G hi,
+// G lo, X hi, X lo); G is scaled by the device-resident gradient scale, X by kActScale, the accumulator is scaled back
+// when it is flushed; the bias gradient is the exact fp32 column sum of the rows as they pass through the registers.
+__global__ void __launch_bounds__(256, 1) k_wgrad_tc_split(const WgradBatch batch, const float* __restrict__ g_scale_dev) {
   extern __shared__ uint8_t smem_raw[];
   const int cpp = batch.ctas_per_prob;
   const WgradParams p = batch.prob[blockIdx.x / cpp];
   const int cta_in_prob = blockIdx.x % cpp;
-  constexpr uint32_t IDESC_MM = make_idesc(1, 128, 128, 1, 1);
+  constexpr uint32_t IDESC_MM = make_idesc(0, 128, 128, 1, 1);  // fp16 operands
+  const float g_scale = *g_scale_dev;
+  const float out_scale = 1.f / (g_scale * kActScale);
   const uint32_t s0 = smem_u32(smem_raw);
   const uint32_t sbase = (s0 + 1023u) & ~1023u;
   uint8_t* sp = smem_raw + (sbase - s0);
@@ -688,8 +695,8 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc_split(const WgradBatch batc
       for (int u = 0; u < 8; ++u) {
         acc_b.x += vg[u].x; acc_b.y += vg[u].y; acc_b.z += vg[u].z; acc_b.w += vg[u].w;
       }
-      coop_rows_store_split<8>(t_gh, t_gl, warp * 16 + 8 * half, lane, vg);
-      coop_rows_store_split<8>(t_xh, t_xl, warp * 16 + 8 * half, lane, vx);
+      coop_rows_store_split<8>(t_gh, t_gl, warp * 16 + 8 * half, lane, vg, g_scale);
+      coop_rows_store_split<8>(t_xh, t_xl, warp * 16 + 8 * half, lane, vx, kActScale);
     }
     fence_proxy_async();
     fence_before_sync();
@@ -723,9 +730,9 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc_split(const WgradBatch batc
     wait_ld();
     float* dst = p.dW + (size_t)n * p.ldo + 64 * hh;
 #pragma unroll
-    for (int t = 0; t < 32; ++t) atomicAdd(dst + t, __uint_as_float(r0[t]));
+    for (int t = 0; t < 32; ++t) atomicAdd(dst + t, __uint_as_float(r0[t]) * out_scale);
 #pragma unroll
-    for (int t = 0; t < 32; ++t) atomicAdd(dst + 32 + t, __uint_as_float(r1[t]));
+    for (int t = 0; t < 32; ++t) atomicAdd(dst + 32 + t, __uint_as_float(r1[t]) * out_scale);
     if (p.db) {
       atomicAdd(p.db + 4 * lane + 0, acc_b.x);
       atomicAdd(p.db + 4 * lane + 1, acc_b.y);
@@ -740,24 +747,41 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc_split(const WgradBatch batc
 
 WgradParams wgrad_problem(const float* G, int ldg, const float* X, int ldx, float* dW, int ldo, float* db, long long rows);
 // plain-pointer front ends for gmp.cu (which does not see the packed-operand headers)
-int pack_blocks_bf16split_ptrs(const float* const* W, const int* ld, int n, uint8_t* out, cudaStream_t st) {
-  PackList pl;
-  pl.n = n;
-  for (int i = 0; i < n; ++i) {
-    pl.w[i] = W[i];
-    pl.ld[i] = ld[i];
-  }
-  return pack_blocks_bf16split(pl, out, st);
+// power-of-two scale for the gradient operands of one GMP backward: 2^floor(log2(8 / max|g_out|)) (1 when g_out is 0):
+// the largest upstream gradient lands at 4..8, four decades of headroom below the fp16 maximum for what LayerNorm
+// backward, the weights and the per-node sums over up to ~250 edges multiply it by (beyond that a value saturates, it
+// never becomes infinite); fp16 subnormals bound the ABSOLUTE error of the lo piece by 2^-25 scaled = 2^-28 of the maximum
+__global__ void k_amax(const float* __restrict__ g, long long n, unsigned* __restrict__ amax_bits) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(g[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));  // non-negative floats order like their bits
 }
-int wgrad_tc_split_batch(const WgradParams* probs, int nprob, cudaStream_t st);
-int wgrad_tc_split3(const float* const* G, const int* ldg, const float* const* X, const int* ldx, float* const* dW, const int* ldo,
-                    float* const* db, int nprob, long long rows, cudaStream_t st) {
-  WgradParams pr[6];
-  for (int i = 0; i < nprob; ++i) pr[i] = wgrad_problem(G[i], ldg[i], X[i], ldx[i], dW[i], ldo[i], db[i], rows);
-  return wgrad_tc_split_batch(pr, nprob, st);
+__global__ void k_grad_scale(const unsigned* __restrict__ amax_bits, float* __restrict__ scale) {
+  const float m = __uint_as_float(*amax_bits);
+  *scale = (m > 0.f && isfinite(m)) ? exp2f(floorf(log2f(8.f / m))) : 1.f;
+}
+int grad_scale_for(const float* g_out, long long n, float* scratch2 /* [2]: amax bits, scale */, cudaStream_t st) {
+  BSMS_CUDA(cudaMemsetAsync(scratch2, 0, 2 * sizeof(float), st));
+  ProfScope ps_(PK_OTHER, st);
+  k_amax<<<(int)std::min<long long>((n + 2047) / 2048, 592), 256, 0, st>>>(g_out, n, reinterpret_cast<unsigned*>(scratch2));
+  BSMS_LAUNCHED();
+  k_grad_scale<<<1, 1, 0, st>>>(reinterpret_cast<const unsigned*>(scratch2), scratch2 + 1);
+  BSMS_LAUNCHED();
+  return BSMS_OK;
 }
 
-int wgrad_tc_split_batch(const WgradParams* probs, int nprob, cudaStream_t st) {
+int wgrad_tc_split_batch(const WgradParams* probs, int nprob, const float* g_scale_dev, cudaStream_t st);
+int wgrad_tc_split3(const float* const* G, const int* ldg, const float* const* X, const int* ldx, float* const* dW, const int* ldo,
+                    float* const* db, int nprob, long long rows, const float* g_scale_dev, cudaStream_t st) {
+  WgradParams pr[6];
+  for (int i = 0; i < nprob; ++i) pr[i] = wgrad_problem(G[i], ldg[i], X[i], ldx[i], dW[i], ldo[i], db[i], rows);
+  return wgrad_tc_split_batch(pr, nprob, g_scale_dev, st);
+}
+
+int wgrad_tc_split_batch(const WgradParams* probs, int nprob, const float* g_scale_dev, cudaStream_t st) {
   if (nprob == 0 || probs[0].rows == 0) return BSMS_OK;
   WgradBatch b;
   b.nprob = nprob;
@@ -770,7 +794,7 @@ int wgrad_tc_split_batch(const WgradParams* probs, int nprob, cudaStream_t st) {
   const size_t smem = 1024 + 4 * kWBlk + 64;
   BSMS_CUDA(cudaFuncSetAttribute(k_wgrad_tc_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope ps_(PK_WGRAD, st);
-  k_wgrad_tc_split<<<b.ctas_per_prob * nprob, 256, smem, st>>>(b);
+  k_wgrad_tc_split<<<b.ctas_per_prob * nprob, 256, smem, st>>>(b, g_scale_dev);
   BSMS_LAUNCHED();
   return BSMS_OK;
 }
