@@ -59,6 +59,16 @@ k_edge_combine(const float* __restrict__ PsPd, const float* __restrict__ pos, in
   st4(A0 + row * D + lane * 4, make_float4(v[0], v[1], v[2], v[3]));
 }
 
+// warp max of |v| -> one atomicMax of its float bits into `slot` (skipped when the slot already holds as much): the
+// tensor-core backward of the fp32-parity mode scales every gradient operand by a power of two derived from this
+__device__ __forceinline__ void publish_amax4(unsigned* slot, const float4& v) {
+  float m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f && __float_as_uint(m) > *reinterpret_cast<volatile unsigned*>(slot))
+    atomicMax(slot, __float_as_uint(m));
+}
+
 __device__ __forceinline__ void ln_stats(const float4& y, float& mean, float& rstd) {
   float s = warp_sum(y.x + y.y + y.z + y.w);
   mean = s * (1.f / D);
@@ -111,7 +121,7 @@ k_ln_residual(const float* __restrict__ Yn, const float* __restrict__ x, const f
 // upstream row is g[b*N + idx[e]] for edge rows (gather of the aggregated gradient) or g[row].
 __global__ void __launch_bounds__(256)
 k_ln_bwd(const float* __restrict__ Y, const float* __restrict__ g, int ldg, const int32_t* __restrict__ idx,
-         int rows_per_b, int g_rows_per_b, float* __restrict__ gY, long long rows) {
+         int rows_per_b, int g_rows_per_b, float* __restrict__ gY, long long rows, unsigned* __restrict__ amax = nullptr) {
   const int lane = threadIdx.x & 31;
   long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= rows) return;
@@ -127,8 +137,10 @@ k_ln_bwd(const float* __restrict__ Y, const float* __restrict__ g, int ldg, cons
   float4 yh = make_float4((y.x - mean) * rstd, (y.y - mean) * rstd, (y.z - mean) * rstd, (y.w - mean) * rstd);
   float c1 = warp_sum(gv.x + gv.y + gv.z + gv.w) * (1.f / D);
   float c2 = warp_sum(gv.x * yh.x + gv.y * yh.y + gv.z * yh.z + gv.w * yh.w) * (1.f / D);
-  st4(gY + r * D + lane * 4, make_float4(rstd * (gv.x - c1 - yh.x * c2), rstd * (gv.y - c1 - yh.y * c2),
-                                         rstd * (gv.z - c1 - yh.z * c2), rstd * (gv.w - c1 - yh.w * c2)));
+  const float4 o = make_float4(rstd * (gv.x - c1 - yh.x * c2), rstd * (gv.y - c1 - yh.y * c2),
+                               rstd * (gv.z - c1 - yh.z * c2), rstd * (gv.w - c1 - yh.w * c2));
+  st4(gY + r * D + lane * 4, o);
+  if (amax) publish_amax4(amax, o);
 }
 
 // gPsPd[b,n,0:128]  = sum_{k in row_s(n)} gU0[b*E + s2d[k]]   (gradient reaching Ps through x_i gathers)
@@ -136,7 +148,7 @@ k_ln_bwd(const float* __restrict__ Y, const float* __restrict__ g, int ldg, cons
 __global__ void __launch_bounds__(256)
 k_edge_grad_segsum(const float* __restrict__ gU0, const int32_t* __restrict__ rowptr_d,
                    const int32_t* __restrict__ rowptr_s, const int32_t* __restrict__ s2d, float* __restrict__ gPsPd,
-                   int B, int N, int E) {
+                   int B, int N, int E, unsigned* __restrict__ amax2 = nullptr) {
   const int lane = threadIdx.x & 31;
   long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (gw >= (long long)B * N) return;
@@ -153,6 +165,10 @@ k_edge_grad_segsum(const float* __restrict__ gU0, const int32_t* __restrict__ ro
   }
   st4(gPsPd + gw * 256 + lane * 4, as);
   st4(gPsPd + gw * 256 + 128 + lane * 4, ad);
+  if (amax2) {
+    publish_amax4(amax2, as);
+    publish_amax4(amax2 + 1, ad);
+  }
 }
 
 // gW1[:, 0:P+1] += gU0^T fiber ; gb1 += colsum(gU0).  Block = 128 threads (one per channel),
@@ -208,10 +224,10 @@ int launch_ln_residual(const float* Yn, const float* x, const float* skip, float
   BSMS_LAUNCHED();
   return BSMS_OK;
 }
-int launch_ln_bwd_rows(const float* Y, const float* g, int ldg, float* gY, long long rows, cudaStream_t st) {
+int launch_ln_bwd_rows(const float* Y, const float* g, int ldg, float* gY, long long rows, cudaStream_t st, unsigned* amax = nullptr) {
   if (rows == 0) return BSMS_OK;
   ProfScope ps_(PK_LN_BWD, st);
-  k_ln_bwd<<<ceil_div(rows * 32, 256), 256, 0, st>>>(Y, g, ldg, nullptr, 0, 0, gY, rows);
+  k_ln_bwd<<<ceil_div(rows * 32, 256), 256, 0, st>>>(Y, g, ldg, nullptr, 0, 0, gY, rows, amax);
   BSMS_LAUNCHED();
   return BSMS_OK;
 }
@@ -291,10 +307,10 @@ struct PackList;
 struct WgradParams;
 int lin_tc2_split(const float* X0, int ldx0, int NB, const uint8_t* const* blocks, int b_mn, const float* bias, int relu,
                   const float* mask, int ldmask, const float* add0, int ldadd0, const float* add1, int ldadd1, float* Y0,
-                  int ldy0, float* Y1, int ldy1, long long rows, int kind, const float* a_scale_dev, cudaStream_t st);
-int grad_scale_for(const float* g_out, long long n, float* scratch2, cudaStream_t st);
+                  int ldy0, float* Y1, int ldy1, long long rows, int kind, const unsigned* a_amax_dev, unsigned* y_amax_dev,
+                  cudaStream_t st);
 int wgrad_tc_split3(const float* const* G, const int* ldg, const float* const* X, const int* ldx, float* const* dW, const int* ldo,
-                    float* const* db, int nprob, long long rows, const float* g_scale_dev, cudaStream_t st);
+                    float* const* db, int nprob, long long rows, const unsigned* g_amax_dev, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------------------------
 // Backward of the fp32-parity tensor-core mode (BSMS_MODE_FP16X3) ON TENSOR CORES.  Every GEMM of the backward — the
@@ -302,8 +318,9 @@ int wgrad_tc_split3(const float* const* G, const int* ldg, const float* const* X
 // two-way fp16 splits of both operands (22 significant bits, three MMAs per K step; a two-way bf16 split, 16 bits, was
 // measured first and missed the 5e-4 gradient bar: 1.4e-3), with fp32 accumulation and fp32 tensors in HBM.  Operands are
 // scaled by powers of two so that the fp16 pieces stay normal: weights by 2^8 and activations by 2^4 as in the forward
-// (whose packed weight images are reused from `saved`), gradients by ONE device-resident scale per call derived from
-// max|g_out| (their magnitude follows the caller's loss scaling).  Per-edge activations are
+// (whose packed weight images are reused from `saved`); every GRADIENT tensor by its own scale, derived from the
+// max |value| its producing kernel records in a device slot (gradient magnitudes follow the caller's loss scaling and
+// grow through LayerNorm backward and the per-node sums; one scale per call was measured first and clipped: 8e-3).  Per-edge activations are
 // recomputed into the workspace (never kept between forward and backward); the node-level tensors come from
 // `saved`.  Non-GEMM kernels (gather/combine, LayerNorm backward, segment sums) are the exact-fp32 ones of the
 // fp32 mode.  Reference: src/ops/basic.py:48-98 differentiated by autograd.
@@ -333,78 +350,74 @@ static int backward_x3(const bsms_level_plan* pl, const bsms_gmp_weights* w, con
   float* Gn2 = ar.take<float>(Rn * D);
   float* g_aggr = ar.take<float>(Rn * D);
   float* gPsPd = ar.take<float>(Rn * 256);
-  float* gscale2 = ar.take<float>(2);  // [amax bits, scale]
+  unsigned* am = ar.take<unsigned>(16);  // max |value| (float bits) of every gradient tensor, recorded by its producer
   if (!ar.ok()) {
     set_error("bsms_gmp_backward: workspace too small for the tensor-core fp32-parity backward");
     return BSMS_EWORKSPACE;
   }
+  BSMS_CUDA(cudaMemsetAsync(am, 0, 16 * sizeof(unsigned), st));
   // the forward's fp16-split weight images ([hi | lo], 64 KB per block) sit behind the node tensors in `saved`, in the
   // block order of gmp_tc.cu: W2, W3, W4, W1s, W1d, V1a, V1b, V2, V3, V4
   const uint8_t* packs = reinterpret_cast<const uint8_t*>(sv.take<uint8_t>(1));
   enum { kW2 = 0, kW3, kW4, kW1s, kW1d, kV1a, kV1b, kV2, kV3, kV4 };
-  BSMS_TRY(grad_scale_for(g_out, Rn * D, gscale2, st));
-  const float* gs = gscale2 + 1;
   auto blk = [&](int i) { return (const uint8_t*)(packs + (size_t)i * 65536); };
-  // act: the A operand is an activation (static scale); otherwise a gradient (device scale)
+  // one 128 -> 128 layer: a_slot >= 0: the A operand is the gradient tensor whose max sits in am[a_slot], -1: an
+  // activation (static scale); y_slot >= 0: record max |output| in am[y_slot]
   auto lin1 = [&](const float* X, int ldx, int wi, int b_mn, const float* bias, int relu, const float* mask, const float* add,
-                  float* Yo, long long rows, int kind, bool act = false) {
+                  float* Yo, long long rows, int kind, int a_slot, int y_slot) {
     const uint8_t* b[1] = {blk(wi)};
     return lin_tc2_split(X, ldx, 1, b, b_mn, bias, relu, mask, D, add, D, nullptr, 0, Yo, D, nullptr, 0, rows, kind,
-                         act ? nullptr : gs, st);
+                         a_slot >= 0 ? am + a_slot : nullptr, y_slot >= 0 ? am + y_slot : nullptr, st);
   };
-  auto wg = [&](const float* G, int ldg, const float* X, int ldx, float* dW, int ldo, float* db, long long rows) {
+  auto wg = [&](const float* G, int ldg, const float* X, int ldx, float* dW, int ldo, float* db, long long rows, int g_slot) {
     const float* Gp[1] = {G};
     const float* Xp[1] = {X};
     float* dWp[1] = {dW};
     float* dbp[1] = {db};
-    return wgrad_tc_split3(Gp, &ldg, Xp, &ldx, dWp, &ldo, dbp, 1, rows, gs, st);
+    return wgrad_tc_split3(Gp, &ldg, Xp, &ldx, dWp, &ldo, dbp, 1, rows, am + g_slot, st);
   };
-  // ---- node MLP backward
-  BSMS_TRY(launch_ln_bwd_rows(Yn, g_out, D, Gn1, Rn, st));
-  BSMS_TRY(wg(Gn1, D, N3, D, gr->w_node[3], D, gr->b_node[3], Rn));
-  BSMS_TRY(lin1(Gn1, D, kV4, 1, nullptr, 0, N3, nullptr, Gn2, Rn, PK_DGRAD));
-  BSMS_TRY(wg(Gn2, D, N2, D, gr->w_node[2], D, gr->b_node[2], Rn));
-  BSMS_TRY(lin1(Gn2, D, kV3, 1, nullptr, 0, N2, nullptr, Gn1, Rn, PK_DGRAD));
-  BSMS_TRY(wg(Gn1, D, N1, D, gr->w_node[1], D, gr->b_node[1], Rn));
-  BSMS_TRY(lin1(Gn1, D, kV2, 1, nullptr, 0, N1, nullptr, Gn2, Rn, PK_DGRAD));  // Gn2 = gradient at the first node layer's output
+  // ---- node MLP backward                                                   slots: 0 Gn1, 1 Gn2, 2 Gn1', 3 G at layer-0 output
+  BSMS_TRY(launch_ln_bwd_rows(Yn, g_out, D, Gn1, Rn, st, am + 0));
+  BSMS_TRY(wg(Gn1, D, N3, D, gr->w_node[3], D, gr->b_node[3], Rn, 0));
+  BSMS_TRY(lin1(Gn1, D, kV4, 1, nullptr, 0, N3, nullptr, Gn2, Rn, PK_DGRAD, 0, 1));
+  BSMS_TRY(wg(Gn2, D, N2, D, gr->w_node[2], D, gr->b_node[2], Rn, 1));
+  BSMS_TRY(lin1(Gn2, D, kV3, 1, nullptr, 0, N2, nullptr, Gn1, Rn, PK_DGRAD, 1, 2));
+  BSMS_TRY(wg(Gn1, D, N1, D, gr->w_node[1], D, gr->b_node[1], Rn, 2));
+  BSMS_TRY(lin1(Gn1, D, kV2, 1, nullptr, 0, N1, nullptr, Gn2, Rn, PK_DGRAD, 2, 3));  // Gn2 = gradient at the first node layer's output
+  BSMS_TRY(wg(Gn2, D, x, D, gr->w_node[0], 2 * D, gr->b_node[0], Rn, 3));
+  BSMS_TRY(wg(Gn2, D, aggr, D, gr->w_node[0] + D, 2 * D, nullptr, Rn, 3));
   {
-    const float* Gp[2] = {Gn2, Gn2};
-    const int ldg[2] = {D, D};
-    const float* Xp[2] = {x, aggr};
-    const int ldx[2] = {D, D};
-    float* dWp[2] = {gr->w_node[0], gr->w_node[0] + D};
-    const int ldo[2] = {2 * D, 2 * D};
-    float* dbp[2] = {gr->b_node[0], nullptr};
-    BSMS_TRY(wgrad_tc_split3(Gp, ldg, Xp, ldx, dWp, ldo, dbp, 2, Rn, gs, st));
     // [g_x | g_aggr] = Gn2 [V1a | V1b]; g_x also takes the residual path's g_out
     const uint8_t* b[2] = {blk(kV1a), blk(kV1b)};
-    BSMS_TRY(lin_tc2_split(Gn2, D, 2, b, 1, nullptr, 0, nullptr, 0, g_out, D, nullptr, 0, g_x, D, g_aggr, D, Rn, PK_DGRAD, gs, st));
+    BSMS_TRY(lin_tc2_split(Gn2, D, 2, b, 1, nullptr, 0, nullptr, 0, g_out, D, nullptr, 0, g_x, D, g_aggr, D, Rn, PK_DGRAD, am + 3,
+                           nullptr, st));
   }
   // ---- edge MLP: recompute a0..a2, y; LayerNorm backward; three (weight gradient, data gradient) pairs
+  //                                                                           slots: 5 Ge1, 6 Ge2, 7 Ge1', 9 gPs, 10 gPd
   if (Re > 0) {
     if (P == 1) BSMS_TRY(edge_combine<1>(PsPd, pos, pos_batched, pl, w->w_edge[0], nullptr, A0, B, st));
     if (P == 2) BSMS_TRY(edge_combine<2>(PsPd, pos, pos_batched, pl, w->w_edge[0], nullptr, A0, B, st));
     if (P == 3) BSMS_TRY(edge_combine<3>(PsPd, pos, pos_batched, pl, w->w_edge[0], nullptr, A0, B, st));
-    BSMS_TRY(lin1(A0, D, kW2, 0, w->b_edge[1], 1, nullptr, nullptr, A1, Re, PK_EDGE_FWD_GEMM, true));
-    BSMS_TRY(lin1(A1, D, kW3, 0, w->b_edge[2], 1, nullptr, nullptr, A2, Re, PK_EDGE_FWD_GEMM, true));
-    BSMS_TRY(lin1(A2, D, kW4, 0, w->b_edge[3], 0, nullptr, nullptr, Y, Re, PK_EDGE_FWD_GEMM, true));
+    BSMS_TRY(lin1(A0, D, kW2, 0, w->b_edge[1], 1, nullptr, nullptr, A1, Re, PK_EDGE_FWD_GEMM, -1, -1));
+    BSMS_TRY(lin1(A1, D, kW3, 0, w->b_edge[2], 1, nullptr, nullptr, A2, Re, PK_EDGE_FWD_GEMM, -1, -1));
+    BSMS_TRY(lin1(A2, D, kW4, 0, w->b_edge[3], 0, nullptr, nullptr, Y, Re, PK_EDGE_FWD_GEMM, -1, -1));
     {
       ProfScope ps_(PK_LN_BWD, st);
-      k_ln_bwd<<<ceil_div(Re * 32, 256), 256, 0, st>>>(Y, g_aggr, D, pl->dst_d, E, N, Ge1, Re);
+      k_ln_bwd<<<ceil_div(Re * 32, 256), 256, 0, st>>>(Y, g_aggr, D, pl->dst_d, E, N, Ge1, Re, am + 5);
     }
     BSMS_LAUNCHED();
-    BSMS_TRY(wg(Ge1, D, A2, D, gr->w_edge[3], D, gr->b_edge[3], Re));
-    BSMS_TRY(lin1(Ge1, D, kW4, 1, nullptr, 0, A2, nullptr, Ge2, Re, PK_DGRAD));
-    BSMS_TRY(wg(Ge2, D, A1, D, gr->w_edge[2], D, gr->b_edge[2], Re));
-    BSMS_TRY(lin1(Ge2, D, kW3, 1, nullptr, 0, A1, nullptr, Ge1, Re, PK_DGRAD));
-    BSMS_TRY(wg(Ge1, D, A0, D, gr->w_edge[1], D, gr->b_edge[1], Re));
-    BSMS_TRY(lin1(Ge1, D, kW2, 1, nullptr, 0, A0, nullptr, Ge2, Re, PK_DGRAD));  // Ge2 = gradient at the edge input a0's pre-activation
+    BSMS_TRY(wg(Ge1, D, A2, D, gr->w_edge[3], D, gr->b_edge[3], Re, 5));
+    BSMS_TRY(lin1(Ge1, D, kW4, 1, nullptr, 0, A2, nullptr, Ge2, Re, PK_DGRAD, 5, 6));
+    BSMS_TRY(wg(Ge2, D, A1, D, gr->w_edge[2], D, gr->b_edge[2], Re, 6));
+    BSMS_TRY(lin1(Ge2, D, kW3, 1, nullptr, 0, A1, nullptr, Ge1, Re, PK_DGRAD, 6, 7));
+    BSMS_TRY(wg(Ge1, D, A0, D, gr->w_edge[1], D, gr->b_edge[1], Re, 7));
+    BSMS_TRY(lin1(Ge1, D, kW2, 1, nullptr, 0, A0, nullptr, Ge2, Re, PK_DGRAD, 7, -1));  // Ge2 = gradient at the edge input a0's pre-activation
     if (P == 1) BSMS_TRY(fiber_wgrad<1>(Ge2, pos, pos_batched, pl, gr->w_edge[0], gr->b_edge[0], B, st));
     if (P == 2) BSMS_TRY(fiber_wgrad<2>(Ge2, pos, pos_batched, pl, gr->w_edge[0], gr->b_edge[0], B, st));
     if (P == 3) BSMS_TRY(fiber_wgrad<3>(Ge2, pos, pos_batched, pl, gr->w_edge[0], gr->b_edge[0], B, st));
     {
       ProfScope ps_(PK_EDGE_GRAD_SEGSUM, st);
-      k_edge_grad_segsum<<<ceil_div(Rn * 32, 256), 256, 0, st>>>(Ge2, pl->rowptr_d, pl->rowptr_s, pl->s2d, gPsPd, B, N, E);
+      k_edge_grad_segsum<<<ceil_div(Rn * 32, 256), 256, 0, st>>>(Ge2, pl->rowptr_d, pl->rowptr_s, pl->s2d, gPsPd, B, N, E, am + 9);
     }
     BSMS_LAUNCHED();
     // node-level gradients of the first edge layer: gW1s += gPs^T x, gW1d += gPd^T x, g_x += gPs W1s + gPd W1d
@@ -415,9 +428,9 @@ static int backward_x3(const bsms_level_plan* pl, const bsms_gmp_weights* w, con
     float* dWp[2] = {gr->w_edge[0] + (P + 1), gr->w_edge[0] + (P + 1 + D)};
     const int ldo[2] = {ldw1, ldw1};
     float* dbp[2] = {nullptr, nullptr};
-    BSMS_TRY(wgrad_tc_split3(Gp, ldg, Xp, ldx, dWp, ldo, dbp, 2, Rn, gs, st));
-    BSMS_TRY(lin1(gPsPd, 256, kW1s, 1, nullptr, 0, nullptr, g_x, g_x, Rn, PK_DGRAD));
-    BSMS_TRY(lin1(gPsPd + 128, 256, kW1d, 1, nullptr, 0, nullptr, g_x, g_x, Rn, PK_DGRAD));
+    BSMS_TRY(wgrad_tc_split3(Gp, ldg, Xp, ldx, dWp, ldo, dbp, 2, Rn, am + 9, st));
+    BSMS_TRY(lin1(gPsPd, 256, kW1s, 1, nullptr, 0, nullptr, g_x, g_x, Rn, PK_DGRAD, 9, -1));
+    BSMS_TRY(lin1(gPsPd + 128, 256, kW1d, 1, nullptr, 0, nullptr, g_x, g_x, Rn, PK_DGRAD, 10, -1));
   }
   return BSMS_OK;
 }

@@ -193,8 +193,10 @@ struct Lin2Params {
   int ldadd[2];
   float* Y[2];
   int ldy[2];
-  float a_scale;             // SPLIT: power-of-two scale of the A operand (activations: kActScale) ...
-  const float* a_scale_dev;  // ... or, when non-null, read from device memory (gradients: one scale per GMP backward)
+  float a_scale;                // SPLIT: power-of-two scale of the A operand (activations: kActScale) ...
+  const unsigned* a_amax_dev;   // ... or, when non-null, derived from the operand's max |value| (float bits) in device memory:
+                                // gradients, whose magnitude follows the loss — the producer of the tensor recorded it
+  unsigned* y_amax_dev;         // when non-null: atomicMax of the float bits of max |stored output| (the next GEMM's a_amax_dev)
   float* ln_out;  // NB == 1: ln_out = LN(y) + res0 (+ res1), rows of 128
   const float* res0;
   const float* res1;
@@ -207,13 +209,29 @@ struct Lin2Params {
 // back in the epilogue; weight blocks are the [hi | lo] pairs of k_pack_weights<2> (scale kWScale); the A scale is
 // kActScale for activations and a device-resident scale for gradients (whose magnitude follows the loss).  KB must be 1
 // (a K = 256 layer is two launches, the second adding the first).
+// power-of-two scale that puts a tensor's largest magnitude (float bits in device memory) at 512..1024: the hi piece of
+// the fp16 split is normal for everything down to max * 2^-24 and nothing overflows (accumulation is fp32 in TMEM)
+__device__ __forceinline__ float split_scale(unsigned amax_bits) {
+  const float m = __uint_as_float(amax_bits);
+  return (m > 0.f && m < 3.0e38f) ? exp2f(floorf(log2f(1024.f / m))) : 1.f;
+}
+// max over the warp, then one atomicMax of the float bits (non-negative floats order like their bit patterns) — skipped
+// when the slot already holds something at least as large
+__device__ __forceinline__ void publish_amax(unsigned* slot, float m) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f && __float_as_uint(m) > *reinterpret_cast<volatile unsigned*>(slot))
+    atomicMax(slot, __float_as_uint(m));
+}
+
 template <int SPLIT>
 __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_lin2(const Lin2Params p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t NSP = SPLIT ? 2 : 1;
   constexpr uint32_t WB = NSP * kWBlk;  // bytes of one packed weight block
   const uint32_t idesc = make_idesc(SPLIT ? 0u : 1u, 128, 128, 0, p.b_mn ? 1u : 0u);
-  const float a_scale = SPLIT ? (p.a_scale_dev ? *p.a_scale_dev : p.a_scale) : 1.f;
+  const float a_scale = SPLIT ? (p.a_amax_dev ? split_scale(*p.a_amax_dev) : p.a_scale) : 1.f;
+  float y_amax = 0.f;
   const float out_scale = SPLIT ? 1.f / (a_scale * kWScale) : 1.f;
   const uint32_t s0 = smem_u32(smem_raw);
   const uint32_t sbase = (s0 + 1023u) & ~1023u;
@@ -359,6 +377,7 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_lin2(const Lin2Params p)
             v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
           }
           st4(yo + row * p.ldy[nb], v);
+          if (p.y_amax_dev) y_amax = fmaxf(y_amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
           if (p.ln_out) {
             const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.f / 128.f);
             const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
@@ -377,6 +396,7 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_lin2(const Lin2Params p)
       __syncthreads();  // the staging tile is rewritten by the next block / the next tile's A tiles
     }
   }
+  if (p.y_amax_dev) publish_amax(p.y_amax_dev, y_amax);
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, ncols);
@@ -590,7 +610,8 @@ int lin_tc2(const float* X0, int ldx0, const float* X1, int ldx1, int KB, int NB
   p.res0 = res0;
   p.res1 = res1;
   p.a_scale = 1.f;
-  p.a_scale_dev = nullptr;
+  p.a_amax_dev = nullptr;
+  p.y_amax_dev = nullptr;
   p.rows = rows;
   p.ntiles = ceil_div(rows, 128);
   const int nblk = KB * NB;
@@ -606,11 +627,13 @@ int lin_tc2(const float* X0, int ldx0, const float* X1, int ldx1, int KB, int NB
 
 // The same layer in the two-way fp16 split arithmetic (22 significant bits per operand, three MMAs per K step): the
 // tensor-core form of the fp32-parity mode's backward GEMMs.  blocks: the [hi | lo] pairs the forward packed
-// (k_pack_weights<2>); a_scale_dev (device, power of two) scales a gradient operand, null = activations (kActScale);
+// (k_pack_weights<2>); a_amax_dev: device slot holding the float bits of max |A| (a gradient operand: its scale is derived
+// from it), null = activations (kActScale); y_amax_dev: slot that receives max |output| (block 0) for the next GEMM;
 // K = 128 only (NB = 1 or 2).
 int lin_tc2_split(const float* X0, int ldx0, int NB, const uint8_t* const* blocks, int b_mn, const float* bias, int relu,
                   const float* mask, int ldmask, const float* add0, int ldadd0, const float* add1, int ldadd1, float* Y0,
-                  int ldy0, float* Y1, int ldy1, long long rows, int kind, const float* a_scale_dev, cudaStream_t st) {
+                  int ldy0, float* Y1, int ldy1, long long rows, int kind, const unsigned* a_amax_dev, unsigned* y_amax_dev,
+                  cudaStream_t st) {
   if (rows == 0) return BSMS_OK;
   Lin2Params p;
   p.X[0] = X0; p.X[1] = nullptr;
@@ -630,7 +653,8 @@ int lin_tc2_split(const float* X0, int ldx0, int NB, const uint8_t* const* block
   p.ln_out = nullptr;
   p.res0 = p.res1 = nullptr;
   p.a_scale = kActScale;
-  p.a_scale_dev = a_scale_dev;
+  p.a_amax_dev = a_amax_dev;
+  p.y_amax_dev = y_amax_dev;
   p.rows = rows;
   p.ntiles = ceil_div(rows, 128);
   const int grid = std::min(sm_count(), p.ntiles);
@@ -647,13 +671,13 @@ int lin_tc2_split(const float* X0, int ldx0, int NB, const uint8_t* const* block
 // step, 22 significant bits): the weight gradient of the fp32-parity mode on tensor cores.  One 128 KB stage (G hi,
 // G lo, X hi, X lo); G is scaled by the device-resident gradient scale, X by kActScale, the accumulator is scaled back
 // when it is flushed; the bias gradient is the exact fp32 column sum of the rows as they pass through the registers.
-__global__ void __launch_bounds__(256, 1) k_wgrad_tc_split(const WgradBatch batch, const float* __restrict__ g_scale_dev) {
+__global__ void __launch_bounds__(256, 1) k_wgrad_tc_split(const WgradBatch batch, const unsigned* __restrict__ g_amax_dev) {
   extern __shared__ uint8_t smem_raw[];
   const int cpp = batch.ctas_per_prob;
   const WgradParams p = batch.prob[blockIdx.x / cpp];
   const int cta_in_prob = blockIdx.x % cpp;
   constexpr uint32_t IDESC_MM = make_idesc(0, 128, 128, 1, 1);  // fp16 operands
-  const float g_scale = *g_scale_dev;
+  const float g_scale = split_scale(g_amax_dev[blockIdx.x / batch.ctas_per_prob]);  // one slot per problem
   const float out_scale = 1.f / (g_scale * kActScale);
   const uint32_t s0 = smem_u32(smem_raw);
   const uint32_t sbase = (s0 + 1023u) & ~1023u;
@@ -747,41 +771,16 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc_split(const WgradBatch batc
 
 WgradParams wgrad_problem(const float* G, int ldg, const float* X, int ldx, float* dW, int ldo, float* db, long long rows);
 // plain-pointer front ends for gmp.cu (which does not see the packed-operand headers)
-// power-of-two scale for the gradient operands of one GMP backward: 2^floor(log2(8 / max|g_out|)) (1 when g_out is 0):
-// the largest upstream gradient lands at 4..8, four decades of headroom below the fp16 maximum for what LayerNorm
-// backward, the weights and the per-node sums over up to ~250 edges multiply it by (beyond that a value saturates, it
-// never becomes infinite); fp16 subnormals bound the ABSOLUTE error of the lo piece by 2^-25 scaled = 2^-28 of the maximum
-__global__ void k_amax(const float* __restrict__ g, long long n, unsigned* __restrict__ amax_bits) {
-  float m = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    m = fmaxf(m, fabsf(g[i]));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));  // non-negative floats order like their bits
-}
-__global__ void k_grad_scale(const unsigned* __restrict__ amax_bits, float* __restrict__ scale) {
-  const float m = __uint_as_float(*amax_bits);
-  *scale = (m > 0.f && isfinite(m)) ? exp2f(floorf(log2f(8.f / m))) : 1.f;
-}
-int grad_scale_for(const float* g_out, long long n, float* scratch2 /* [2]: amax bits, scale */, cudaStream_t st) {
-  BSMS_CUDA(cudaMemsetAsync(scratch2, 0, 2 * sizeof(float), st));
-  ProfScope ps_(PK_OTHER, st);
-  k_amax<<<(int)std::min<long long>((n + 2047) / 2048, 592), 256, 0, st>>>(g_out, n, reinterpret_cast<unsigned*>(scratch2));
-  BSMS_LAUNCHED();
-  k_grad_scale<<<1, 1, 0, st>>>(reinterpret_cast<const unsigned*>(scratch2), scratch2 + 1);
-  BSMS_LAUNCHED();
-  return BSMS_OK;
-}
-
-int wgrad_tc_split_batch(const WgradParams* probs, int nprob, const float* g_scale_dev, cudaStream_t st);
+// g_amax_dev: nprob CONSECUTIVE device slots, slot i = float bits of max |G_i|
+int wgrad_tc_split_batch(const WgradParams* probs, int nprob, const unsigned* g_amax_dev, cudaStream_t st);
 int wgrad_tc_split3(const float* const* G, const int* ldg, const float* const* X, const int* ldx, float* const* dW, const int* ldo,
-                    float* const* db, int nprob, long long rows, const float* g_scale_dev, cudaStream_t st) {
+                    float* const* db, int nprob, long long rows, const unsigned* g_amax_dev, cudaStream_t st) {
   WgradParams pr[6];
   for (int i = 0; i < nprob; ++i) pr[i] = wgrad_problem(G[i], ldg[i], X[i], ldx[i], dW[i], ldo[i], db[i], rows);
-  return wgrad_tc_split_batch(pr, nprob, g_scale_dev, st);
+  return wgrad_tc_split_batch(pr, nprob, g_amax_dev, st);
 }
 
-int wgrad_tc_split_batch(const WgradParams* probs, int nprob, const float* g_scale_dev, cudaStream_t st) {
+int wgrad_tc_split_batch(const WgradParams* probs, int nprob, const unsigned* g_amax_dev, cudaStream_t st) {
   if (nprob == 0 || probs[0].rows == 0) return BSMS_OK;
   WgradBatch b;
   b.nprob = nprob;
@@ -794,7 +793,7 @@ int wgrad_tc_split_batch(const WgradParams* probs, int nprob, const float* g_sca
   const size_t smem = 1024 + 4 * kWBlk + 64;
   BSMS_CUDA(cudaFuncSetAttribute(k_wgrad_tc_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope ps_(PK_WGRAD, st);
-  k_wgrad_tc_split<<<b.ctas_per_prob * nprob, 256, smem, st>>>(b, g_scale_dev);
+  k_wgrad_tc_split<<<b.ctas_per_prob * nprob, 256, smem, st>>>(b, g_amax_dev);
   BSMS_LAUNCHED();
   return BSMS_OK;
 }
