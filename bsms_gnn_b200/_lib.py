@@ -46,7 +46,7 @@ EXPORTS = [
     "bsms_cal_ew", "bsms_permute_ew", "bsms_edge_conv", "bsms_conv_down_pool", "bsms_unpool_conv_up",
     "bsms_gather_rows", "bsms_unpool_rows", "bsms_gmp_workspace_bytes", "bsms_gmp_saved_bytes", "bsms_gmp_forward",
     "bsms_gmp_backward", "bsms_launch_count", "bsms_prof_enable", "bsms_prof_collect",
-    "bsms_debug_edge_stage", "bsms_masked_rmse", "bsms_clip_adamw_step", "bsms_inject_noise",
+    "bsms_debug_edge_stage", "bsms_debug_lin_split", "bsms_masked_rmse", "bsms_clip_adamw_step", "bsms_inject_noise",
     "bsms_gmp_packed_bytes", "bsms_gmp_pack", "bsms_gmp_forward_packed",
     "bsms_components_host", "bsms_bistride_level_host", "bsms_host_free",
     "bsms_ipc_alloc", "bsms_ipc_free", "bsms_ipc_export", "bsms_ipc_open", "bsms_ipc_close", "bsms_halo_exchange",
@@ -90,6 +90,7 @@ def _load():
     f64 = C.c_double
     lib.bsms_masked_rmse.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp]
     lib.bsms_clip_adamw_step.argtypes = [vp, vp, vp, vp, i64, vp, vp, f64, f64, f64, f64, f64, f64, f64, f64, i32, vp]
+    lib.bsms_debug_lin_split.argtypes = [vp, i64, vp, i32, vp, i32, vp, vp, vp]
     lib.bsms_inject_noise.argtypes = [vp, i32, vp, i32, vp, i64, P(C.c_float), C.c_float, C.c_uint64, C.c_uint64, vp]
     lib.bsms_gmp_packed_bytes.restype = sz
     lib.bsms_gmp_packed_bytes.argtypes = []

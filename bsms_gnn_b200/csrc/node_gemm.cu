@@ -837,4 +837,28 @@ int wgrad_tc(const float* G, int ldg, const float* X, int ldx, float* dW, int ld
   return wgrad_tc_batch(&p, 1, st);
 }
 
+// Test hook: Y = ((X W^T) or (X W)) [. (mask > 0)] on the split-operand tensor-core layer; a_is_grad: scale X from its
+// own max |value| (computed here), else the static activation scale.  scratch: 64 KB + 64 bytes.
+__global__ void k_dbg_amax(const float* __restrict__ g, long long n, unsigned* __restrict__ slot) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(g[i]));
+  bsms::publish_amax(slot, m);
+}
 }  // namespace bsms
+extern "C" int bsms_debug_lin_split(const float* X, int64_t rows, const float* W, int32_t b_mn, const float* mask,
+                                    int32_t a_is_grad, float* Y, void* scratch, void* stream) {
+  using namespace bsms;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* pack = (uint8_t*)scratch;
+  unsigned* slot = (unsigned*)(pack + 2 * kWBlk);
+  PackList pl;
+  pl.n = 1;
+  pl.w[0] = W;
+  pl.ld[0] = kD;
+  k_pack_weights<2><<<1, 256, 0, st>>>(pl, pack);
+  BSMS_CUDA(cudaMemsetAsync(slot, 0, 16, st));
+  if (a_is_grad) k_dbg_amax<<<64, 256, 0, st>>>(X, rows * kD, slot);
+  const uint8_t* b[1] = {pack};
+  return lin_tc2_split(X, kD, 1, b, b_mn, nullptr, 0, mask, kD, nullptr, 0, nullptr, 0, Y, kD, nullptr, 0, rows, PK_OTHER,
+                       a_is_grad ? slot : nullptr, slot + 1, st);
+}

@@ -306,6 +306,12 @@ int bsms_bistride_level_host(const int64_t* flat_edge, int64_t n_edges, int64_t 
                              int64_t* n_edges_out);
 void bsms_host_free(void* p);
 
+/* Test hook for the split-operand tensor-core layer of the fp32-parity backward: Y[rows,128] = X W^T (b_mn = 0) or
+ * X W (b_mn = 1), optionally masked by (mask > 0); a_is_grad != 0 scales X by its own max (gradient operands), else
+ * by the static activation scale.  scratch: 64 KB + 64 bytes of device memory. */
+int bsms_debug_lin_split(const float* X, int64_t rows, const float* W, int32_t b_mn, const float* mask,
+                         int32_t a_is_grad, float* Y, void* scratch, void* stream);
+
 /* Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline pass).
  * Kinds: 0 edge-MLP forward GEMM/chain, 1 node-level forward GEMMs, 2 edge gather+combine,
  * 3 LayerNorm+segment-sum, 4 dgrad, 5 wgrad, 6 LayerNorm backward, 7 edge-gradient segment sums,
