@@ -51,6 +51,7 @@ EXPORTS = [
     "bsms_components_host", "bsms_bistride_level_host", "bsms_host_free",
     "bsms_ipc_alloc", "bsms_ipc_free", "bsms_ipc_export", "bsms_ipc_open", "bsms_ipc_close", "bsms_halo_exchange",
     "bsms_encode_in", "bsms_dense128_packed_bytes", "bsms_dense128_pack", "bsms_dense128_stack", "bsms_decode_out",
+    "bsms_set_deterministic", "bsms_get_deterministic",
 ]
 
 
@@ -86,6 +87,10 @@ def _load():
                                       i32, i32, i32, vp, sz, vp]
     lib.bsms_launch_count.restype = i64
     lib.bsms_launch_count.argtypes = []
+    lib.bsms_set_deterministic.restype = None
+    lib.bsms_set_deterministic.argtypes = [i32]
+    lib.bsms_get_deterministic.restype = i32
+    lib.bsms_get_deterministic.argtypes = []
     lib.bsms_debug_edge_stage.argtypes = [P(LevelPlanC), P(GmpWeightsC), vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, sz, vp]
     f64 = C.c_double
     lib.bsms_masked_rmse.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp]

@@ -122,15 +122,38 @@ static inline int gemm_kn(const float* X, int ldx, int K, const float* W, int ld
   return BSMS_OK;
 }
 
+// Ordered commit of per-CTA partial sums (the deterministic option, bsms_set_deterministic): a CTA takes a ticket when
+// it STARTS (so every lower ticket is already running: no dependence on the dispatch order), works on the chunk of that
+// ticket, and adds its partial sums only after every lower ticket has committed — each address then receives its
+// addends in one fixed order.  t[0]: next ticket, t[1]: tickets committed (both zeroed by the caller).
+__device__ __forceinline__ int ordered_ticket(int* t, int* s_slot) {
+  if (threadIdx.x == 0) *s_slot = atomicAdd(&t[0], 1);
+  __syncthreads();
+  return *s_slot;
+}
+__device__ __forceinline__ void ordered_wait(int* t, int ticket) {
+  if (threadIdx.x == 0) {
+    while (atomicAdd(&t[1], 0) != ticket) __nanosleep(64);
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void ordered_done(int* t) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(&t[1], 1);
+}
+
 // dW[n*ldo + k] += sum_{m in chunk} G[m*ldg + n] * X[m*ldx + k]   (n, k in [0,128))
 __global__ void __launch_bounds__(256)
 k_wgrad(const float* __restrict__ G, int ldg, const float* __restrict__ X, int ldx, float* __restrict__ dW, int ldo,
-        float* __restrict__ db, long long M, int rows_per_cta) {
+        float* __restrict__ db, long long M, int rows_per_cta, int* __restrict__ order) {
   __shared__ __align__(16) float Gs[GBK][128 + GPAD];
   __shared__ __align__(16) float Xs[GBK][128 + GPAD];
+  __shared__ int s_ticket;
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const int bid = order ? ordered_ticket(order, &s_ticket) : (int)blockIdx.x;
+  long long r0 = (long long)bid * rows_per_cta;
   long long r1 = min(r0 + rows_per_cta, M);
   float acc[8][8];
 #pragma unroll
@@ -171,6 +194,7 @@ k_wgrad(const float* __restrict__ G, int ldg, const float* __restrict__ X, int l
     }
     __syncthreads();
   }
+  if (order) ordered_wait(order, bid);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     int n = (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
@@ -181,16 +205,18 @@ k_wgrad(const float* __restrict__ G, int ldg, const float* __restrict__ X, int l
     }
   }
   if (db && tid < 128) atomicAdd(&db[tid], bsum);
+  if (order) ordered_done(order);
 }
 
+// order: nullptr, or two zeroed ints for the ordered (deterministic) commit
 static inline int wgrad(const float* G, int ldg, const float* X, int ldx, float* dW, int ldo, float* db, long long M,
-                        cudaStream_t st) {
+                        cudaStream_t st, int* order = nullptr) {
   if (M == 0) return BSMS_OK;
   long long per = (M + 148 * 4 - 1) / (148 * 4);
   per = (per + GBK - 1) / GBK * GBK;
   if (per < 256) per = 256;
   ProfScope ps(PK_WGRAD, st);
-  k_wgrad<<<ceil_div(M, per), 256, 0, st>>>(G, ldg, X, ldx, dW, ldo, db, M, (int)per);
+  k_wgrad<<<ceil_div(M, per), 256, 0, st>>>(G, ldg, X, ldx, dW, ldo, db, M, (int)per, order);
   BSMS_LAUNCHED();
   return BSMS_OK;
 }

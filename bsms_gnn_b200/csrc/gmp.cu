@@ -177,9 +177,11 @@ template <int P>
 __global__ void __launch_bounds__(128)
 k_fiber_wgrad(const float* __restrict__ gU0, const float* __restrict__ pos, int pos_batched,
               const int32_t* __restrict__ src_d, const int32_t* __restrict__ dst_d, float* __restrict__ gW1,
-              float* __restrict__ gb1, int B, int N, int E, int rows_per_block) {
+              float* __restrict__ gb1, int B, int N, int E, int rows_per_block, int* __restrict__ order) {
+  __shared__ int s_ticket;
   const int c = threadIdx.x;
-  long long r0 = (long long)blockIdx.x * rows_per_block;
+  const int bid = order ? ordered_ticket(order, &s_ticket) : (int)blockIdx.x;
+  long long r0 = (long long)bid * rows_per_block;
   long long r1 = min(r0 + rows_per_block, (long long)B * E);
   float acc[P + 1], accb = 0.f;
 #pragma unroll
@@ -201,9 +203,11 @@ k_fiber_wgrad(const float* __restrict__ gU0, const float* __restrict__ pos, int 
     for (int p = 0; p <= P; ++p) acc[p] += g * fib[p];
   }
   const int ldw = 2 * D + P + 1;
+  if (order) ordered_wait(order, bid);
 #pragma unroll
   for (int p = 0; p <= P; ++p) atomicAdd(&gW1[(size_t)c * ldw + p], acc[p]);
   atomicAdd(&gb1[c], accb);
+  if (order) ordered_done(order);
 }
 
 // g_x = g_out + gcat[:, 0:128]   (residual + node-MLP input path); later GEMM accumulates the edge path
@@ -259,14 +263,14 @@ static int edge_combine(const float* PsPd, const float* pos, int pos_batched, co
 
 template <int P>
 static int fiber_wgrad(const float* gU0, const float* pos, int pos_batched, const bsms_level_plan* pl, float* gW1,
-                       float* gb1, int B, cudaStream_t st) {
+                       float* gb1, int B, cudaStream_t st, int* order = nullptr) {
   long long rows = (long long)B * pl->n_edges;
   if (rows == 0) return BSMS_OK;
   int rpb = (int)std::max<long long>(64, (rows + 148 * 8 - 1) / (148 * 8));
   {
     ProfScope ps_(PK_WGRAD, st);
     k_fiber_wgrad<P><<<ceil_div(rows, rpb), 128, 0, st>>>(gU0, pos, pos_batched, pl->src_d, pl->dst_d, gW1, gb1, B,
-                                                          pl->n_nodes, pl->n_edges, rpb);
+                                                          pl->n_nodes, pl->n_edges, rpb, order);
   }
   BSMS_LAUNCHED();
   return BSMS_OK;
@@ -512,6 +516,14 @@ static Fp32Acts carve(Arena& ar, long long Rn, long long Re, bool keep, bool edg
 
 using namespace bsms;
 
+// Deterministic option: bitwise run-to-run reproducible forward and backward.  It is served by the exact-fp32 mode,
+// whose segment sums walk the CSR rows in order without atomics; with the switch on, its two split-over-rows weight
+// gradient kernels commit their partial sums in ticket order (gemm_fp32.cuh ordered_*), and the tensor-core modes —
+// which reduce with red.add in arrival order — are refused instead of silently falling back.
+static int g_deterministic = 0;
+extern "C" void bsms_set_deterministic(int32_t on) { g_deterministic = on ? 1 : 0; }
+extern "C" int32_t bsms_get_deterministic(void) { return g_deterministic; }
+
 extern "C" size_t bsms_gmp_saved_bytes(int32_t B, int32_t N) {
   size_t Rn = (size_t)B * N;
   auto f = [](size_t n) { return align_up(n * sizeof(float), 256); };
@@ -582,6 +594,8 @@ static int gmp_forward_impl(const bsms_level_plan* pl, const bsms_gmp_weights* w
     set_error("bsms_gmp_forward: workspace too small");
     return BSMS_EWORKSPACE;
   }
+  BSMS_CHECK_ARG(!g_deterministic || mode == BSMS_MODE_FP32,
+                 "bsms_gmp_forward: the deterministic option (bsms_set_deterministic) is served by BSMS_MODE_FP32 only");
   if (mode != BSMS_MODE_FP32)
     return gmp_forward_tc(pl, w, x, pos, pos_batched, skip, out, saved, B, P, mode, ws, ws_bytes, st, (const uint8_t*)packed);
   const long long Rn = (long long)B * pl->n_nodes, Re = (long long)B * pl->n_edges;
@@ -610,6 +624,8 @@ extern "C" int bsms_gmp_backward(const bsms_level_plan* pl, const bsms_gmp_weigh
     set_error("bsms_gmp_backward: workspace too small");
     return BSMS_EWORKSPACE;
   }
+  BSMS_CHECK_ARG(!g_deterministic || mode == BSMS_MODE_FP32,
+                 "bsms_gmp_backward: the deterministic option (bsms_set_deterministic) is served by BSMS_MODE_FP32 only");
   if (mode == BSMS_MODE_BF16)
     return gmp_backward_tc(pl, w, x, pos, pos_batched, saved, g_out, g_x, gr, B, P, ws, ws_bytes, st);
   // fp32-parity tensor-core mode with the forward's node-level intermediates at hand: every GEMM on tcgen05
@@ -632,6 +648,14 @@ extern "C" int bsms_gmp_backward(const bsms_level_plan* pl, const bsms_gmp_weigh
   float* Gn2 = ar.take<float>(Rn * D);
   float* gcat = ar.take<float>(Rn * 256);
   float* gPsPd = ar.take<float>(Rn * 256);
+  // deterministic option: one (next ticket, committed) pair per split-over-rows weight-gradient launch
+  int* order = nullptr;
+  if (g_deterministic) {
+    order = ar.take<int>(32);
+    BSMS_CHECK_ARG(ar.ok(), "bsms_gmp_backward: workspace too small");
+    BSMS_CUDA(cudaMemsetAsync(order, 0, 32 * sizeof(int), st));
+  }
+  auto ord = [&](int i) { return order ? order + 2 * i : nullptr; };
   // ---- recompute forward, keeping every (node-level) activation
   if (!have_saved)
     BSMS_TRY(fp32_forward(pl, w, x, pos, pos_batched, B, P, a, st, fused ? BSMS_MODE_BF16 : BSMS_MODE_FP32, wpack));
@@ -641,15 +665,15 @@ extern "C" int bsms_gmp_backward(const bsms_level_plan* pl, const bsms_gmp_weigh
     k_ln_bwd<<<ceil_div(Rn * 32, 256), 256, 0, st>>>(a.Yn, g_out, D, nullptr, 0, 0, Gn1, Rn);
   }
   BSMS_LAUNCHED();
-  BSMS_TRY(wgrad(Gn1, D, a.N3, D, gr->w_node[3], D, gr->b_node[3], Rn, st));
+  BSMS_TRY(wgrad(Gn1, D, a.N3, D, gr->w_node[3], D, gr->b_node[3], Rn, st, ord(0)));
   BSMS_TRY(gemm_kn(Gn1, D, D, w->w_node[3], D, a.N3, D, Gn2, D, Rn, D, GEMM_MASK, st));
-  BSMS_TRY(wgrad(Gn2, D, a.N2, D, gr->w_node[2], D, gr->b_node[2], Rn, st));
+  BSMS_TRY(wgrad(Gn2, D, a.N2, D, gr->w_node[2], D, gr->b_node[2], Rn, st, ord(1)));
   BSMS_TRY(gemm_kn(Gn2, D, D, w->w_node[2], D, a.N2, D, Gn1, D, Rn, D, GEMM_MASK, st));
-  BSMS_TRY(wgrad(Gn1, D, a.N1, D, gr->w_node[1], D, gr->b_node[1], Rn, st));
+  BSMS_TRY(wgrad(Gn1, D, a.N1, D, gr->w_node[1], D, gr->b_node[1], Rn, st, ord(2)));
   BSMS_TRY(gemm_kn(Gn1, D, D, w->w_node[1], D, a.N1, D, Gn2, D, Rn, D, GEMM_MASK, st));
   // layer 0 of the node MLP: input [x | aggr]
-  BSMS_TRY(wgrad(Gn2, D, x, D, gr->w_node[0], 2 * D, gr->b_node[0], Rn, st));
-  BSMS_TRY(wgrad(Gn2, D, a.aggr, D, gr->w_node[0] + D, 2 * D, nullptr, Rn, st));
+  BSMS_TRY(wgrad(Gn2, D, x, D, gr->w_node[0], 2 * D, gr->b_node[0], Rn, st, ord(3)));
+  BSMS_TRY(wgrad(Gn2, D, a.aggr, D, gr->w_node[0] + D, 2 * D, nullptr, Rn, st, ord(4)));
   BSMS_TRY(gemm_kn(Gn2, D, D, w->w_node[0], 2 * D, nullptr, 0, gcat, 256, Rn, 256, 0, st));
   {
     ProfScope ps_(PK_OTHER, st);
@@ -666,15 +690,15 @@ extern "C" int bsms_gmp_backward(const bsms_level_plan* pl, const bsms_gmp_weigh
       k_ln_bwd<<<ceil_div(Re * 32, 256), 256, 0, st>>>(a.Y, gcat + 128, 256, pl->dst_d, E, N, Ge1, Re);
     }
     BSMS_LAUNCHED();
-    BSMS_TRY(wgrad(Ge1, D, a.A2, D, gr->w_edge[3], D, gr->b_edge[3], Re, st));
+    BSMS_TRY(wgrad(Ge1, D, a.A2, D, gr->w_edge[3], D, gr->b_edge[3], Re, st, ord(5)));
     BSMS_TRY(gemm_kn(Ge1, D, D, w->w_edge[3], D, a.A2, D, Ge2, D, Re, D, GEMM_MASK, st));
-    BSMS_TRY(wgrad(Ge2, D, a.A1, D, gr->w_edge[2], D, gr->b_edge[2], Re, st));
+    BSMS_TRY(wgrad(Ge2, D, a.A1, D, gr->w_edge[2], D, gr->b_edge[2], Re, st, ord(6)));
     BSMS_TRY(gemm_kn(Ge2, D, D, w->w_edge[2], D, a.A1, D, Ge1, D, Re, D, GEMM_MASK, st));
-    BSMS_TRY(wgrad(Ge1, D, a.A0, D, gr->w_edge[1], D, gr->b_edge[1], Re, st));
+    BSMS_TRY(wgrad(Ge1, D, a.A0, D, gr->w_edge[1], D, gr->b_edge[1], Re, st, ord(7)));
     BSMS_TRY(gemm_kn(Ge1, D, D, w->w_edge[1], D, a.A0, D, Ge2, D, Re, D, GEMM_MASK, st));  // Ge2 = gU0
-    if (P == 1) BSMS_TRY(fiber_wgrad<1>(Ge2, pos, pos_batched, pl, gr->w_edge[0], gr->b_edge[0], B, st));
-    if (P == 2) BSMS_TRY(fiber_wgrad<2>(Ge2, pos, pos_batched, pl, gr->w_edge[0], gr->b_edge[0], B, st));
-    if (P == 3) BSMS_TRY(fiber_wgrad<3>(Ge2, pos, pos_batched, pl, gr->w_edge[0], gr->b_edge[0], B, st));
+    if (P == 1) BSMS_TRY(fiber_wgrad<1>(Ge2, pos, pos_batched, pl, gr->w_edge[0], gr->b_edge[0], B, st, ord(8)));
+    if (P == 2) BSMS_TRY(fiber_wgrad<2>(Ge2, pos, pos_batched, pl, gr->w_edge[0], gr->b_edge[0], B, st, ord(8)));
+    if (P == 3) BSMS_TRY(fiber_wgrad<3>(Ge2, pos, pos_batched, pl, gr->w_edge[0], gr->b_edge[0], B, st, ord(8)));
     {
       ProfScope ps_(PK_EDGE_GRAD_SEGSUM, st);
       k_edge_grad_segsum<<<ceil_div(Rn * 32, 256), 256, 0, st>>>(Ge2, pl->rowptr_d, pl->rowptr_s, pl->s2d, gPsPd, B, N, E);
@@ -683,8 +707,8 @@ extern "C" int bsms_gmp_backward(const bsms_level_plan* pl, const bsms_gmp_weigh
   }
   if (Re > 0) {
     // node-level layer-0 gradients: gW1s += gPs^T x, gW1d += gPd^T x, g_x += gPs W1s + gPd W1d
-    BSMS_TRY(wgrad(gPsPd, 256, x, D, gr->w_edge[0] + (P + 1), ldw1, nullptr, Rn, st));
-    BSMS_TRY(wgrad(gPsPd + 128, 256, x, D, gr->w_edge[0] + (P + 1 + D), ldw1, nullptr, Rn, st));
+    BSMS_TRY(wgrad(gPsPd, 256, x, D, gr->w_edge[0] + (P + 1), ldw1, nullptr, Rn, st, ord(9)));
+    BSMS_TRY(wgrad(gPsPd + 128, 256, x, D, gr->w_edge[0] + (P + 1 + D), ldw1, nullptr, Rn, st, ord(10)));
     BSMS_TRY(gemm_kn(gPsPd, 256, D, w->w_edge[0] + (P + 1), ldw1, nullptr, 0, g_x, D, Rn, D, GEMM_ACCUM, st));
     BSMS_TRY(gemm_kn(gPsPd + 128, 256, D, w->w_edge[0] + (P + 1 + D), ldw1, nullptr, 0, g_x, D, Rn, D, GEMM_ACCUM, st));
   }

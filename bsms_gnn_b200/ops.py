@@ -40,6 +40,18 @@ def set_default_mode(mode: str):
     _DEFAULT_MODE = mode
 
 
+def set_deterministic(on: bool):
+    """Bitwise run-to-run reproducible forward and backward (the role torch.use_deterministic_algorithms plays for the
+    reference, whose scatter_add_ is order-dependent on CUDA).  While on, every GMP block runs the exact-fp32 kernels
+    — CSR segment sums in row order, no atomics — with ordered weight-gradient commits (bsms_set_deterministic),
+    whatever mode it was built with; the transfer operators are order-fixed in every mode.  About 9x slower than bf16."""
+    lib.bsms_set_deterministic(1 if on else 0)
+
+
+def is_deterministic() -> bool:
+    return bool(lib.bsms_get_deterministic())
+
+
 def _as_b3(x: torch.Tensor, what: str):
     """[N,C] | [B,N,C] fp32 CUDA -> contiguous [B,N,C] view + original rank."""
     if x.dim() not in (2, 3):
@@ -168,7 +180,10 @@ class GMP(nn.Module):
             raise RuntimeError("pos and x disagree on the batch size")
         pos = pos.detach().to(torch.float32).contiguous()
         skip3 = None if skip is None else _as_b3(skip, "skip")
-        out = _GMPFunction.apply(x3, pos, skip3, level, self.mode, self.pos_dim, self._packed_weights(), *self._params())
+        if lib.bsms_get_deterministic():
+            out = _GMPFunction.apply(x3, pos, skip3, level, _lib.MODE_FP32, self.pos_dim, None, *self._params())
+        else:
+            out = _GMPFunction.apply(x3, pos, skip3, level, self.mode, self.pos_dim, self._packed_weights(), *self._params())
         return out if x.dim() == 3 else out.squeeze(0)
 
     def _packed_weights(self):

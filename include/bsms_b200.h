@@ -312,6 +312,16 @@ void bsms_host_free(void* p);
 int bsms_debug_lin_split(const float* X, int64_t rows, const float* W, int32_t b_mn, const float* mask,
                          int32_t a_is_grad, float* Y, void* scratch, void* stream);
 
+/* Deterministic option (process-wide switch, default off): bitwise run-to-run reproducible results.  Served by
+ * BSMS_MODE_FP32 — its segment sums walk CSR rows in order without atomics, and with the switch on its
+ * split-over-rows weight-gradient kernels commit their partial sums in a fixed (ticket) order.  While the switch is on,
+ * bsms_gmp_forward / bsms_gmp_backward in a tensor-core mode return BSMS_EINVAL (those modes reduce with red.add in
+ * arrival order); the transfer operators are order-fixed CSR sums in every mode.  The reference offers
+ * torch.use_deterministic_algorithms for the same purpose (its scatter_add_ is otherwise order-dependent on CUDA,
+ * src/utils/basic.py:287-343). */
+void bsms_set_deterministic(int32_t on);
+int32_t bsms_get_deterministic(void);
+
 /* Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline pass).
  * Kinds: 0 edge-MLP forward GEMM/chain, 1 node-level forward GEMMs, 2 edge gather+combine,
  * 3 LayerNorm+segment-sum, 4 dgrad, 5 wgrad, 6 LayerNorm backward, 7 edge-gradient segment sums,

@@ -1,0 +1,56 @@
+"""The deterministic option (ops.set_deterministic / bsms_set_deterministic): forward, data gradient and every parameter
+gradient of the whole processor are BITWISE identical from run to run, and still within the fp32 tolerances of the
+reference golden.  The tensor-core modes reduce with red.add in arrival order and must refuse to run under the switch
+at the C-ABI (the Python host routes every block to the exact-fp32 kernels instead)."""
+import pytest
+import torch
+
+from oracle import bsms_oracle as O
+from tests.util import bsgmp_inputs, load_hier, load_npz, max_rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _step(model, h, m_ids, m_gs, ps):
+    model.zero_grad()
+    hg = h.clone().requires_grad_(True)
+    out = model(hg, m_ids, m_gs, ps)
+    out.square().mean().backward()
+    return [out.detach().clone(), hg.grad.clone()] + [p.grad.clone() for _, p in sorted(model.named_parameters())]
+
+
+@pytest.mark.parametrize("case,hname", [("grid44", "grid44"), ("ico3", "ico3")])
+def test_deterministic_option_is_bitwise_reproducible(case, hname):
+    from bsms_gnn_b200 import ops
+    dev = torch.device("cuda:0")
+    rec = load_npz(f"bsgmp_{case}.npz")
+    m_gs, m_ids, pos, d = load_hier(hname)
+    h, ps = bsgmp_inputs(rec, pos, pos.shape[0])
+    model = ops.BSGMP(d, 128, 3, int(rec["P"])).to(dev)  # default (tensor-core) mode: the switch overrides it
+    model.load_state_dict(O.init_params(d, pos_dim=int(rec["P"]), seed=int(rec["seed"])))
+    h, ps = h.to(dev), ps.to(dev)
+    ids, gs = [i.to(dev) for i in m_ids], [g.to(dev) for g in m_gs]
+    assert not ops.is_deterministic()
+    ops.set_deterministic(True)
+    try:
+        assert ops.is_deterministic()
+        runs = [_step(model, h, ids, gs, ps) for _ in range(4)]
+        for k, r in enumerate(runs[1:]):
+            for i, (a, b) in enumerate(zip(runs[0], r)):
+                assert torch.equal(a, b), f"run {k + 1}, tensor {i}: max diff {float((a - b).abs().max()):.3e}"
+        rs = int(rec["row_stride"])
+        assert max_rel(runs[0][0].cpu()[..., ::rs, :], rec["out"]) < 1e-5
+        if "grad_h" in rec.files:
+            assert max_rel(runs[0][1].cpu()[..., ::rs, :], rec["grad_h"]) < 5e-4
+        # the C-ABI itself refuses a tensor-core mode under the switch (no silent change of arithmetic below the host)
+        from bsms_gnn_b200 import _lib, plan as P
+        blk = model.down_gmps[0]
+        x3 = (h if h.dim() == 3 else h.unsqueeze(0)).contiguous()
+        lp = P.level_plan(gs[0], x3.shape[1])
+        with pytest.raises(_lib.BsmsError):
+            ops._GMPFunction.apply(x3, ps.contiguous(), None, lp, _lib.MODE_BF16, blk.pos_dim, None, *blk._params())
+    finally:
+        ops.set_deterministic(False)
+    # informational: how far two default-mode runs are apart
+    a, b = _step(model, h, ids, gs, ps), _step(model, h, ids, gs, ps)
+    print(f"\n[{case}] default mode run-to-run max-rel: out {max_rel(a[0], b[0]):.1e}, grad_h {max_rel(a[1], b[1]):.1e}")
