@@ -49,6 +49,7 @@ EXPORTS = [
     "bsms_debug_edge_stage", "bsms_debug_lin_split", "bsms_masked_rmse", "bsms_clip_adamw_step", "bsms_inject_noise",
     "bsms_gmp_packed_bytes", "bsms_gmp_pack", "bsms_gmp_forward_packed",
     "bsms_components_host", "bsms_bistride_level_host", "bsms_host_free",
+    "bsms_hierarchy_build_host", "bsms_hierarchy_level_host", "bsms_hierarchy_free_host",
     "bsms_ipc_alloc", "bsms_ipc_free", "bsms_ipc_export", "bsms_ipc_open", "bsms_ipc_close", "bsms_halo_exchange",
     "bsms_encode_in", "bsms_dense128_packed_bytes", "bsms_dense128_pack", "bsms_dense128_stack", "bsms_decode_out",
     "bsms_set_deterministic", "bsms_get_deterministic",
@@ -111,6 +112,10 @@ def _load():
     lib.bsms_bistride_level_host.argtypes = [vp, i64, i64, vp, i64, vp, vp, P(i64), P(vp), P(i64)]
     lib.bsms_host_free.argtypes = [vp]
     lib.bsms_host_free.restype = None
+    lib.bsms_hierarchy_build_host.argtypes = [vp, i64, i64, vp, i32, i32, i32, P(vp)]
+    lib.bsms_hierarchy_level_host.argtypes = [vp, i32, P(i64), P(i64), P(vp), P(vp)]
+    lib.bsms_hierarchy_free_host.argtypes = [vp]
+    lib.bsms_hierarchy_free_host.restype = None
     lib.bsms_ipc_alloc.argtypes = [sz, P(vp)]
     lib.bsms_ipc_free.argtypes = [vp]
     lib.bsms_ipc_export.argtypes = [vp, C.c_char_p]

@@ -113,7 +113,7 @@ def bistride_level(flat_edge: np.ndarray, pos: np.ndarray, n: int):
     import os
     if os.environ.get("BSMS_HIERARCHY", "native") == "numpy":
         return bistride_level_numpy(flat_edge, pos, n)
-    return bistride_level_native(flat_edge, pos, n)
+    return bistride_level_native(flat_edge, pos, n)  # "levels" (and the per-level entry point of "native")
 
 
 def bistride_level_numpy(flat_edge: np.ndarray, pos: np.ndarray, n: int):
@@ -141,8 +141,56 @@ def bistride_level_numpy(flat_edge: np.ndarray, pos: np.ndarray, n: int):
     return keep, new_e
 
 
+class _HierarchyHandle:
+    """Owns one native hierarchy (bsms_hierarchy_build_host); the numpy views handed out keep it alive."""
+
+    def __init__(self, ptr, free):
+        self.ptr, self._free = ptr, free
+
+    def __del__(self):
+        if self.ptr:
+            self._free(self.ptr)
+            self.ptr = None
+
+
+def build_hierarchy_native(flat_edge: np.ndarray, num_layers: int, num_nodes: int, pos: np.ndarray):
+    """All levels in ONE call of the library's host code (csrc/hierarchy_host.cpp bsms_hierarchy_build_host): int32 CSR
+    between levels, parallel union-find, the seed choice in the positions' own floating-point type with numpy's
+    operation order, one-pass kept-row (A+I)^2.  The returned arrays are zero-copy views of the native buffers."""
+    import ctypes as C
+
+    from ._lib import check, lib
+    g = np.ascontiguousarray(np.asarray(flat_edge, dtype=np.int64).reshape(2, -1))
+    p = np.asarray(pos)
+    if p.dtype not in (np.float32, np.float64):
+        p = p.astype(np.float64)
+    p = np.ascontiguousarray(p.reshape(int(num_nodes), -1))
+    h = C.c_void_p()
+    check(lib.bsms_hierarchy_build_host(g.ctypes.data, int(g.shape[1]), int(num_nodes), p.ctypes.data, int(p.shape[1]),
+                                        1 if p.dtype == np.float64 else 0, int(num_layers), C.byref(h)))
+    owner = _HierarchyHandle(h.value, lib.bsms_hierarchy_free_host)
+    m_gs, m_ids = [g], []
+    for lvl in range(1, int(num_layers) + 1):
+        nn, ne, ep, ip = C.c_int64(), C.c_int64(), C.c_void_p(), C.c_void_p()
+        check(lib.bsms_hierarchy_level_host(owner.ptr, lvl, C.byref(nn), C.byref(ne), C.byref(ep), C.byref(ip)))
+
+        def view(addr, count, shape):
+            if count == 0:
+                return np.zeros(shape, dtype=np.int64)
+            buf = (C.c_int64 * count).from_address(addr)
+            buf._bsms_owner = owner  # the numpy view references buf, buf references the handle
+            return np.frombuffer(buf, dtype=np.int64, count=count).reshape(shape)
+        m_gs.append(view(ep.value, 2 * ne.value, (2, ne.value)))
+        m_ids.append(view(ip.value, nn.value, (nn.value,)))
+    return m_gs, m_ids
+
+
 def build_hierarchy(flat_edge: np.ndarray, num_layers: int, num_nodes: int, pos: np.ndarray):
-    """-> (m_gs: list[num_layers+1] of int64 [2,E_l], m_ids: list[num_layers] of int64 [n_{l+1}])."""
+    """-> (m_gs: list[num_layers+1] of int64 [2,E_l], m_ids: list[num_layers] of int64 [n_{l+1}]).
+    BSMS_HIERARCHY = native (default: one native call) | levels (native, level by level with numpy seeds) | numpy."""
+    import os
+    if os.environ.get("BSMS_HIERARCHY", "native") == "native":
+        return build_hierarchy_native(flat_edge, num_layers, num_nodes, pos)
     g = np.asarray(flat_edge, dtype=np.int64).reshape(2, -1)
     pos_l = np.asarray(pos)
     n = int(num_nodes)

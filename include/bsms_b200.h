@@ -306,6 +306,18 @@ int bsms_bistride_level_host(const int64_t* flat_edge, int64_t n_edges, int64_t 
                              int64_t* n_edges_out);
 void bsms_host_free(void* p);
 
+/* The whole hierarchy in one call (replaces BistrideMultiLayerGraph(...).get_multi_layer_graphs(),
+ * src/graph_wrappers/bsms_graph_wrapper.py:9-28, including its seed choice :107-126 in the positions' own
+ * floating-point type and numpy's operation order).  flat_edge int64 [2, n_edges]; pos [n_nodes, pos_dim] float32
+ * (pos_is_f64 = 0) or float64; depth = number of pooling levels.  *handle_out owns the result. */
+int bsms_hierarchy_build_host(const int64_t* flat_edge, int64_t n_edges, int64_t n_nodes, const void* pos,
+                              int32_t pos_dim, int32_t pos_is_f64, int32_t depth, void** handle_out);
+/* level in [1, depth]: its edge list int64 [2, *n_edges_out] (row-major, sorted columns) and the ids of its
+ * *n_nodes_out nodes in level - 1 (ascending).  The pointers stay valid until bsms_hierarchy_free_host. */
+int bsms_hierarchy_level_host(void* handle, int32_t level, int64_t* n_nodes_out, int64_t* n_edges_out,
+                              const int64_t** edges_out, const int64_t** ids_out);
+void bsms_hierarchy_free_host(void* handle);
+
 /* Test hook for the split-operand tensor-core layer of the fp32-parity backward: Y[rows,128] = X W^T (b_mn = 0) or
  * X W (b_mn = 1), optionally masked by (mask > 0); a_is_grad != 0 scales X by its own max (gradient operands), else
  * by the static activation scale.  scratch: 64 KB + 64 bytes of device memory. */

@@ -59,30 +59,81 @@ def test_mesh_sizes():
     assert pos.shape == (162, 3) and meshgen.cells_to_flat_edge(cells).shape == (2, 960)
 
 
+def _many_clusters(dtype, P):
+    """40 small grids of different shapes scattered in space (+ isolated nodes): many clusters, ties, single-node clusters."""
+    rng = np.random.default_rng(5)
+    pos_l, cells_l, off = [], [], 0
+    for k in range(40):
+        nx, ny = int(rng.integers(2, 9)), int(rng.integers(2, 9))
+        p, c = meshgen.tri_grid(nx, ny, seed=k)
+        p = np.concatenate([p, np.zeros((p.shape[0], P - 2), dtype=p.dtype)], 1) if P > 2 else p
+        pos_l.append(p.astype(dtype) + rng.uniform(-50, 50, size=(1, P)).astype(dtype))
+        cells_l.append(c + off)
+        off += p.shape[0]
+    pos_l.append(rng.uniform(-50, 50, size=(3, P)).astype(dtype))  # three isolated nodes
+    return np.concatenate(pos_l), meshgen.cells_to_flat_edge(np.concatenate(cells_l))
+
+
 def test_native_builder_equals_numpy_builder(monkeypatch):
     """csrc/hierarchy_host.cpp against the numpy/scipy implementation: identical ids and identical edge ARRAYS (both
-    emit row-major edges with sorted columns), on a mesh larger than the goldens and on disconnected / directed inputs."""
+    emit row-major edges with sorted columns), on a mesh larger than the goldens and on disconnected / directed inputs.
+    `native` = the whole hierarchy in one native call including the seed choice (float32 and float64 positions, 2-D and
+    3-D); `levels` = native integer work level by level with the numpy seed choice."""
     cases = []
     pos, cells = meshgen.tri_grid(120, 90)
     cases.append((pos, meshgen.cells_to_flat_edge(cells), 5))
+    cases.append((pos.astype(np.float64) * 1.37, meshgen.cells_to_flat_edge(cells), 5))
     pos, cells = meshgen.icosphere(4)
     cases.append((pos, meshgen.cells_to_flat_edge(cells), 4))
     p1, c1 = meshgen.tri_grid(9, 7)
     p2, c2 = meshgen.tri_grid(5, 6, seed=1)
     cases.append((np.concatenate([p1, p2 + 20, np.array([[99.0, 99.0]], dtype=np.float32)]),
                   meshgen.cells_to_flat_edge(np.concatenate([c1, c2 + p1.shape[0]])), 3))  # + one isolated node
+    for dtype, P in [(np.float32, 2), (np.float64, 3), (np.float32, 3)]:
+        pos, fe = _many_clusters(dtype, P)
+        cases.append((pos, fe, 3))
+    # an edge list in random order with duplicates (the level-0 conversion's general path)
+    pos, cells = meshgen.tri_grid(40, 31)
+    fe = meshgen.cells_to_flat_edge(cells)
+    rng = np.random.default_rng(1)
+    fe = np.concatenate([fe, fe[:, :100]], 1)[:, rng.permutation(fe.shape[1] + 100)]
+    cases.append((pos, fe, 4))
     for pos, fe, d in cases:
         monkeypatch.setenv("BSMS_HIERARCHY", "numpy")
         gs_n, ids_n = hierarchy.build_hierarchy(fe, d, pos.shape[0], pos)
-        monkeypatch.setenv("BSMS_HIERARCHY", "native")
-        gs_c, ids_c = hierarchy.build_hierarchy(fe, d, pos.shape[0], pos)
-        for a, b in zip(ids_c, ids_n):
-            assert np.array_equal(a, b)
-        for a, b in zip(gs_c[1:], gs_n[1:]):
-            assert np.array_equal(a, b)
+        for impl in ("native", "levels"):
+            monkeypatch.setenv("BSMS_HIERARCHY", impl)
+            gs_c, ids_c = hierarchy.build_hierarchy(fe, d, pos.shape[0], pos)
+            assert len(gs_c) == d + 1 and len(ids_c) == d
+            for a, b in zip(ids_c, ids_n):
+                assert a.dtype == np.int64 and np.array_equal(a, b), impl
+            for a, b in zip(gs_c[1:], gs_n[1:]):
+                assert a.dtype == np.int64 and np.array_equal(a, b), impl
     # a one-directional chain: nodes the seed cannot reach are in neither parity class
     fe = np.array([[0, 1, 2, 3], [1, 2, 3, 4]])
     pos = np.stack([np.arange(5.0), np.zeros(5)], 1).astype(np.float32)
     k_n, e_n = hierarchy.bistride_level_numpy(fe, pos, 5)
     k_c, e_c = hierarchy.bistride_level_native(fe, pos, 5)
     assert np.array_equal(k_n, k_c) and np.array_equal(e_n, e_c)
+    monkeypatch.setenv("BSMS_HIERARCHY", "numpy")
+    gs_n, ids_n = hierarchy.build_hierarchy(fe, 3, 5, pos)
+    gs_c, ids_c = hierarchy.build_hierarchy_native(fe, 3, 5, pos)
+    for a, b in zip(ids_c + gs_c[1:], ids_n + gs_n[1:]):
+        assert np.array_equal(a, b)
+    # errors: an out-of-range index is reported, not read
+    with pytest.raises(IndexError):
+        hierarchy.build_hierarchy_native(np.array([[0, 1], [1, 7]]), 1, 5, pos)
+
+
+def test_native_views_outlive_the_call():
+    """The arrays handed out are zero-copy views of native buffers; they must stay valid after everything else is gone."""
+    import gc
+    pos, cells = meshgen.tri_grid(30, 30)
+    gs, ids = hierarchy.build_hierarchy_native(meshgen.cells_to_flat_edge(cells), 3, pos.shape[0], pos)
+    want = [g.copy() for g in gs], [i.copy() for i in ids]
+    last_g, last_i = gs[-1], ids[0]
+    del gs, ids
+    gc.collect()
+    junk = [np.zeros(1 << 20, dtype=np.int64) for _ in range(8)]  # churn the allocator
+    assert np.array_equal(last_g, want[0][-1]) and np.array_equal(last_i, want[1][0])
+    del junk
