@@ -202,4 +202,20 @@ struct WgradParams {
   int ntiles;
 };
 
+
+// ---- deterministic option (bsms_set_deterministic) in the bf16 mode: every kernel that finishes with one atomic
+// flush per CTA writes its per-CTA (per-warp) partial sums to a scratch block instead, and one small kernel adds
+// them up in a fixed order (tiles are assigned to CTAs statically, so a CTA's partial is itself reproducible); the
+// two fused edge kernels write their per-edge-row results as rows and order-fixed CSR segment sums replace the
+// red.add reductions into node rows.
+int det_enabled();  // gmp.cu
+constexpr int kDetEdgeBwdStride = 3 * 16384 + 3 * 8 * 128 + 8 * 128 + 8 * 128 * 4;  // gW2..4 | gb2..4 per warp | gb1 per warp | fiber per warp
+constexpr int kDetNodeBwdStride = 3 * 16384 + 3 * 8 * 128;                           // gV2..4 | gc2..4 per warp
+constexpr int kDetWgradStride = 16384 + 2 * 128;                                     // dW | db per thread half
+struct DetSeg {
+  float* dst;  // dst[row * ldd + col] += sum over parts part0..part0+nparts-1 and reps of src[rep][row][col]
+  int src_off, part0, nparts, reps, rows, cols, src_cols, ldd;
+};
+int det_reduce(const float* part, int stride, const DetSeg* segs, int nseg, cudaStream_t st);  // gmp_tc.cu
+size_t det_part_bytes();                                                                       // gmp_tc.cu
 }  // namespace bsms

@@ -37,6 +37,7 @@ struct EdgeChainParams {
   const uint8_t* wpack;  // packed weight images: W2, W3, W4 (bf16) or their hi, lo pairs (fp16x3)
   const uint8_t* bpack;  // the shared bias block of the bf16 mode (k_pack_bias3)
   float* aggr;           // [B*N, 128], zero-initialised
+  float* eout;           // deterministic variant: the normalised edge rows [B*E, 128] leave as rows instead
   int B, N, E;
   long long rows;
   int ntiles;
@@ -354,7 +355,7 @@ __global__ void k_pack_bias3(const float* b2, const float* b3, const float* b4, 
   }
 }
 
-template <bool PROF>
+template <bool PROF, bool DET>
 __global__ void __launch_bounds__(512, 1) k_edge_chain_ws(const EdgeChainParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t IDESC = make_idesc(1, 128, 128);
@@ -599,6 +600,18 @@ __global__ void __launch_bounds__(512, 1) k_edge_chain_ws(const EdgeChainParams 
               }
             }
             __syncwarp();
+            if (DET) {
+              // deterministic variant: no reduction here — the rows leave as rows (256 B per half-warp and row) and
+              // an order-fixed CSR segment sum follows (gmp_tc.cu k_segsum_rows)
+#pragma unroll
+              for (int k0 = 0; k0 < 16; ++k0) {
+                const int rr = 16 * hw + k0;
+                const long long grow = (long long)tile * 128 + q * 32 + rr;
+                const float4 m = *reinterpret_cast<const float4*>(wstage + rr * 64 + ((l16 ^ k0) << 2));
+                if (grow < p.rows) st4(p.eout + grow * 128 + 64 * half + 4 * l16, m);
+              }
+              continue;
+            }
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             int cur = -1;
             float* dstc = p.aggr + 64 * half + 4 * l16;
@@ -665,7 +678,7 @@ int edge_chain_pack_bias(const bsms_gmp_weights* w, uint8_t* bpack, cudaStream_t
 // wpack: the packed weight images (scratch when !prepacked); bpack: 16 KB for the shared bias block (bf16).
 int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* PsPd, const float* pos,
                        int pos_batched, int B, int P, int mode, uint8_t* wpack, float* aggr, float* dbg, int dbg_stage,
-                       cudaStream_t st, bool prepacked, uint8_t* bpack) {
+                       cudaStream_t st, bool prepacked, uint8_t* bpack, float* eout) {
   const long long rows = (long long)B * pl->n_edges;
   if (rows == 0) return BSMS_OK;
   PackList pk;
@@ -686,6 +699,7 @@ int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, con
   p.wpack = wpack;
   p.bpack = bpack;
   p.aggr = aggr;
+  p.eout = eout;
   p.B = B;
   p.N = pl->n_nodes;
   p.E = pl->n_edges;
@@ -724,13 +738,17 @@ int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, con
     }
     if (!prepacked) BSMS_TRY_(edge_chain_pack_bias(w, bpack, st));  // prepacked callers packed it with the weights
     const size_t smem = edge_chain_ws_smem();
-    auto kern = phase_prof ? k_edge_chain_ws<true> : k_edge_chain_ws<false>;
+    auto kern = eout ? k_edge_chain_ws<false, true> : (phase_prof ? k_edge_chain_ws<true, false> : k_edge_chain_ws<false, false>);
     BSMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps_(PK_EDGE_CHAIN, st);
     kern<<<grid, 512, smem, st>>>(p);
     BSMS_LAUNCHED();
     if (report() != BSMS_OK) return BSMS_ECUDA;
   } else {
+    if (eout) {
+      set_error("edge_chain_forward: the deterministic variant exists for the bf16 mode only");
+      return BSMS_EINVAL;
+    }
     if (!prepacked) {
       ProfScope ps_(PK_OTHER, st);
       k_pack_weights<2><<<3, 256, 0, st>>>(pk, wpack);

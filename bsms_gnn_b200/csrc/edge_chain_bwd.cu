@@ -37,6 +37,8 @@ struct EdgeBwdParams {
   const float* g_aggr;   // upstream gradient of aggr, row stride ld_g
   int ld_g;
   float* gPsPd;  // [B*N, 256], zero-initialised; receives gPs | gPd
+  float* g0_rows;  // deterministic variant: the edge-input gradient leaves as rows [B*E, 128] (no scatter) ...
+  float* part;     // ... and the per-CTA sums go to part[blockIdx.x][kDetEdgeBwdStride] (no atomic flush)
   float* gW[3];  // W2, W3, W4 gradients [128,128] (accumulated)
   float* gb[4];  // b1..b4 gradients
   float* gW1;    // mlp_edge layer-0 weight gradient [128, 2*128+P+1]: fiber columns accumulated here
@@ -88,7 +90,7 @@ __device__ __forceinline__ float4 make_fiber(const float* __restrict__ pb, int P
 //    1.3 k cycles shorter, the shadow 1.45 k longer — an MMA pair lasts ~1 k cycles, a batch of gathers ~2 k).
 //  * F2: the epilogue arithmetic uses the packed fp32x2 instructions of sm_100 (FADD2 / FFMA2): the epilogues
 //    are bound by the FMA pipe's issue rate, not by latency.
-template <bool PROF, bool F2>
+template <bool PROF, bool F2, bool DET>
 __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr bool NS = false;  // N-split GEMM groups (two N = 64 halves on their own barriers): measured slower, 8.42 vs 7.91 ms
@@ -577,13 +579,19 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
         const float4 gv = *reinterpret_cast<const float4*>(s_g0 + rr * 128 + ((lane ^ (rr & 31)) << 2));
         const int2 ij = s_ij[rr];
         const float4 f = s_fib[rr];
-        if (ij.x >= 0) red_add_v4(p.gPsPd + (size_t)ij.x * 256 + 4 * lane, gv.x, gv.y, gv.z, gv.w);
-        if (ij.y != cur) {
-          if (cur >= 0) red_add_v4(p.gPsPd + (size_t)cur * 256 + 128 + 4 * lane, run.x, run.y, run.z, run.w);
-          cur = ij.y;
-          run = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (DET) {
+          // deterministic variant: the row leaves as a row; k_edge_grad_segsum forms gPs | gPd in CSR order
+          const long long grow = (long long)tile * 128 + rr;
+          if (grow < p.rows) st4(p.g0_rows + (size_t)grow * 128 + 4 * lane, gv);
+        } else {
+          if (ij.x >= 0) red_add_v4(p.gPsPd + (size_t)ij.x * 256 + 4 * lane, gv.x, gv.y, gv.z, gv.w);
+          if (ij.y != cur) {
+            if (cur >= 0) red_add_v4(p.gPsPd + (size_t)cur * 256 + 128 + 4 * lane, run.x, run.y, run.z, run.w);
+            cur = ij.y;
+            run = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          run.x += gv.x; run.y += gv.y; run.z += gv.z; run.w += gv.w;
         }
-        run.x += gv.x; run.y += gv.y; run.z += gv.z; run.w += gv.w;
         acc_b0.x += gv.x; acc_b0.y += gv.y; acc_b0.z += gv.z; acc_b0.w += gv.w;
         acc_fl[0].x += gv.x * f.x; acc_fl[0].y += gv.y * f.x; acc_fl[0].z += gv.z * f.x; acc_fl[0].w += gv.w * f.x;
         acc_fl[1].x += gv.x * f.y; acc_fl[1].y += gv.y * f.y; acc_fl[1].z += gv.z * f.y; acc_fl[1].w += gv.w * f.y;
@@ -592,7 +600,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
       };
 #pragma unroll 4
       for (int rr = warp * 16; rr < warp * 16 + 16; ++rr) scatter_row(rr);
-      if (cur >= 0) red_add_v4(p.gPsPd + (size_t)cur * 256 + 128 + 4 * lane, run.x, run.y, run.z, run.w);
+      if (!DET && cur >= 0) red_add_v4(p.gPsPd + (size_t)cur * 256 + 128 + 4 * lane, run.x, run.y, run.z, run.w);
     }
     __syncthreads();  // the staging tiles / row metadata are rewritten by the next tile
     mark(14);
@@ -605,6 +613,31 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
+  if (DET) {
+    // per-CTA / per-warp partial sums, added up in a fixed order by det_reduce (layout: kDetEdgeBwdStride)
+    float* part = p.part + (size_t)blockIdx.x * kDetEdgeBwdStride;
+#pragma unroll 1
+    for (int l = 0; l < 3; ++l) {
+      float v[64];
+      load_d64(tmem_base + 128 * (l + 1) + lane_off + 64 * h, v);
+      float* dst = part + l * 16384 + r * 128 + 64 * h;
+#pragma unroll
+      for (int q4 = 0; q4 < 16; ++q4) st4(dst + q4 * 4, make_float4(v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]));
+    }
+    float* pb = part + 3 * 16384;
+#pragma unroll
+    for (int l = 1; l < 4; ++l) st4(pb + ((l - 1) * 8 + warp) * 128 + 4 * lane, acc_b[l]);
+    st4(pb + 3 * 8 * 128 + warp * 128 + 4 * lane, acc_b0);
+    float* pf = pb + 4 * 8 * 128 + (warp * 128 + 4 * lane) * 4;  // [warp][channel][fiber component]
+    st4(pf + 0, make_float4(acc_fl[0].x, acc_fl[1].x, acc_fl[2].x, acc_fl[3].x));
+    st4(pf + 4, make_float4(acc_fl[0].y, acc_fl[1].y, acc_fl[2].y, acc_fl[3].y));
+    st4(pf + 8, make_float4(acc_fl[0].z, acc_fl[1].z, acc_fl[2].z, acc_fl[3].z));
+    st4(pf + 12, make_float4(acc_fl[0].w, acc_fl[1].w, acc_fl[2].w, acc_fl[3].w));
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+    return;
+  }
   {
 #pragma unroll 1
     for (int l = 0; l < 3; ++l) {
@@ -646,7 +679,7 @@ size_t edge_chain_bwd_smem() { return 1024 + 6 * kWBlk + 512 * 4 + 128 * 16 * 3 
 // Fused bf16 backward of the edge stage.  gPsPd must be zero-filled; gW/gb/gW1 are accumulated into.
 int edge_chain_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const bsms_gmp_grads* gr, const float* PsPd,
                         const float* pos, int pos_batched, int B, int P, uint8_t* wpack, const float* g_aggr, int ld_g,
-                        float* gPsPd, cudaStream_t st, bool prepacked) {
+                        float* gPsPd, cudaStream_t st, bool prepacked, float* g0_rows, float* part) {
   const long long rows = (long long)B * pl->n_edges;
   if (rows == 0) return BSMS_OK;
   PackList pk;
@@ -673,6 +706,8 @@ int edge_chain_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, co
   p.g_aggr = g_aggr;
   p.ld_g = ld_g;
   p.gPsPd = gPsPd;
+  p.g0_rows = g0_rows;
+  p.part = part;
   p.B = B;
   p.N = pl->n_nodes;
   p.E = pl->n_edges;
@@ -697,12 +732,28 @@ int edge_chain_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, co
   const size_t smem = edge_chain_bwd_smem();
   // BSMS_BWD_F2=0 (development switch) turns the packed fp32x2 epilogue arithmetic off
   static const bool f2 = !(getenv("BSMS_BWD_F2") && atoi(getenv("BSMS_BWD_F2")) == 0);
-  void (*kern)(const EdgeBwdParams) = f2 ? (phase_prof ? k_edge_chain_bwd<true, true> : k_edge_chain_bwd<false, true>)
-                                         : (phase_prof ? k_edge_chain_bwd<true, false> : k_edge_chain_bwd<false, false>);
+  if ((g0_rows == nullptr) != (part == nullptr)) {
+    set_error("edge_chain_backward: the deterministic variant needs both the row buffer and the partial-sum block");
+    return BSMS_EINVAL;
+  }
+  void (*kern)(const EdgeBwdParams) =
+      g0_rows ? k_edge_chain_bwd<false, true, true>
+              : (f2 ? (phase_prof ? k_edge_chain_bwd<true, true, false> : k_edge_chain_bwd<false, true, false>)
+                    : (phase_prof ? k_edge_chain_bwd<true, false, false> : k_edge_chain_bwd<false, false, false>));
   BSMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope ps_(PK_EDGE_CHAIN_BWD, st);
-  kern<<<std::min(sms, p.ntiles), 256, smem, st>>>(p);
+  const int grid = std::min(sms, p.ntiles);
+  kern<<<grid, 256, smem, st>>>(p);
   BSMS_LAUNCHED();
+  if (part) {
+    // ordered reduction of the per-CTA sums into the gradients (layout of the flush above)
+    DetSeg segs[8];
+    for (int l = 0; l < 3; ++l) segs[l] = DetSeg{p.gW[l], l * 16384, 0, grid, 1, 128, 128, 128, 128};
+    for (int l = 1; l < 4; ++l) segs[2 + l] = DetSeg{p.gb[l], 3 * 16384 + (l - 1) * 8 * 128, 0, grid, 8, 1, 128, 128, 128};
+    segs[6] = DetSeg{p.gb[0], 3 * 16384 + 3 * 8 * 128, 0, grid, 8, 1, 128, 128, 128};
+    segs[7] = DetSeg{p.gW1, 3 * 16384 + 4 * 8 * 128, 0, grid, 8, 128, P + 1, 4, 2 * kD + P + 1};
+    return det_reduce(part, kDetEdgeBwdStride, segs, 8, st);
+  }
   if (phase_prof) {  // debug aid: per-phase cycles per tile (thread 0 of every CTA), printed per launch
     unsigned long long h[16];
     BSMS_CUDA(cudaMemcpyAsync(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost, st));

@@ -291,11 +291,11 @@ struct Fp32Acts {
 size_t edge_chain_pack_bytes(int mode);
 int edge_chain_forward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* PsPd, const float* pos,
                        int pos_batched, int B, int P, int mode, uint8_t* wpack, float* aggr, float* dbg, int dbg_stage,
-                       cudaStream_t st, bool prepacked, uint8_t* bpack);
+                       cudaStream_t st, bool prepacked, uint8_t* bpack, float* eout = nullptr);
 
 int edge_chain_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, const bsms_gmp_grads* gr, const float* PsPd,
                         const float* pos, int pos_batched, int B, int P, uint8_t* wpack, const float* g_aggr, int ld_g,
-                        float* gPsPd, cudaStream_t st, bool prepacked);
+                        float* gPsPd, cudaStream_t st, bool prepacked, float* g0_rows = nullptr, float* part = nullptr);
 // tensor-core orchestration of a whole GMP block (gmp_tc.cu)
 int gmp_forward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const float* x, const float* pos, int pos_batched,
                    const float* skip, float* out, float* saved, int B, int P, int mode, void* ws, size_t ws_bytes,
@@ -512,15 +512,31 @@ static Fp32Acts carve(Arena& ar, long long Rn, long long Re, bool keep, bool edg
   }
   return a;
 }
+int launch_edge_grad_segsum(const float* g0_rows, const bsms_level_plan* pl, float* gPsPd, int B, cudaStream_t st) {
+  const long long Rn = (long long)B * pl->n_nodes;
+  if (Rn == 0) return BSMS_OK;
+  ProfScope ps_(PK_EDGE_GRAD_SEGSUM, st);
+  k_edge_grad_segsum<<<ceil_div(Rn * 32, 256), 256, 0, st>>>(g0_rows, pl->rowptr_d, pl->rowptr_s, pl->s2d, gPsPd, B, pl->n_nodes,
+                                                              pl->n_edges);
+  BSMS_LAUNCHED();
+  return BSMS_OK;
+}
 }  // namespace bsms
 
 using namespace bsms;
 
-// Deterministic option: bitwise run-to-run reproducible forward and backward.  It is served by the exact-fp32 mode,
-// whose segment sums walk the CSR rows in order without atomics; with the switch on, its two split-over-rows weight
-// gradient kernels commit their partial sums in ticket order (gemm_fp32.cuh ordered_*), and the tensor-core modes —
-// which reduce with red.add in arrival order — are refused instead of silently falling back.
+// Deterministic option: bitwise run-to-run reproducible forward and backward.
+//  * BSMS_MODE_FP32: its segment sums walk the CSR rows in order without atomics; with the switch on, its two
+//    split-over-rows weight gradient kernels commit their partial sums in ticket order (gemm_fp32.cuh ordered_*).
+//  * BSMS_MODE_BF16: the fused edge kernels write their per-edge-row results as rows and order-fixed CSR segment sums
+//    replace the red.add reductions; every per-CTA flush becomes a partial-sum block + one ordered reduction
+//    (chain.cuh "deterministic option", gmp_tc.cu).
+//  * BSMS_MODE_FP16X3 is refused while the switch is on (the host routes it to BSMS_MODE_FP32, the same 1e-5 grade).
 static int g_deterministic = 0;
+namespace bsms {
+int det_enabled() { return g_deterministic; }
+size_t det_part_bytes();  // gmp_tc.cu: one partial-sum block per CTA of the widest flush
+}  // namespace bsms
 extern "C" void bsms_set_deterministic(int32_t on) { g_deterministic = on ? 1 : 0; }
 extern "C" int32_t bsms_get_deterministic(void) { return g_deterministic; }
 
@@ -537,9 +553,11 @@ extern "C" size_t bsms_gmp_workspace_bytes(int32_t B, int32_t N, int32_t E, int3
   const size_t node_bufs = f(Rn * 256) + 5 * f(Rn * D);  // PsPd, aggr, N1..N3, Yn
   const size_t scratch = 2u << 20;                        // packed weight / bias blocks
   if (mode == BSMS_MODE_BF16 || (mode == BSMS_MODE_FP16X3 && !backward)) {
-    // fused tensor-core path: no per-edge buffer at all
-    if (!backward) return node_bufs + scratch;
-    return node_bufs + 4 * f(Rn * D) + 2 * f(Rn * 256) + scratch;
+    // fused tensor-core path: no per-edge buffer at all — except under the deterministic option (bf16), which moves one
+    // [B*E, 128] row tensor through HBM per direction and keeps one partial-sum block per CTA
+    const size_t det = (g_deterministic && mode == BSMS_MODE_BF16) ? f(Re * D) + (backward ? align_up(det_part_bytes(), 256) : 0) : 0;
+    if (!backward) return node_bufs + scratch + det;
+    return node_bufs + 4 * f(Rn * D) + 2 * f(Rn * 256) + scratch + det;
   }
   // fp32 path (and the fp32 backward the fp16x3 mode uses): per-edge activations are materialised
   size_t fwd = node_bufs + f(Re * D) + scratch;
@@ -594,8 +612,8 @@ static int gmp_forward_impl(const bsms_level_plan* pl, const bsms_gmp_weights* w
     set_error("bsms_gmp_forward: workspace too small");
     return BSMS_EWORKSPACE;
   }
-  BSMS_CHECK_ARG(!g_deterministic || mode == BSMS_MODE_FP32,
-                 "bsms_gmp_forward: the deterministic option (bsms_set_deterministic) is served by BSMS_MODE_FP32 only");
+  BSMS_CHECK_ARG(!g_deterministic || mode != BSMS_MODE_FP16X3,
+                 "bsms_gmp_forward: the deterministic option (bsms_set_deterministic) is served by BSMS_MODE_FP32 and BSMS_MODE_BF16");
   if (mode != BSMS_MODE_FP32)
     return gmp_forward_tc(pl, w, x, pos, pos_batched, skip, out, saved, B, P, mode, ws, ws_bytes, st, (const uint8_t*)packed);
   const long long Rn = (long long)B * pl->n_nodes, Re = (long long)B * pl->n_edges;
@@ -624,8 +642,8 @@ extern "C" int bsms_gmp_backward(const bsms_level_plan* pl, const bsms_gmp_weigh
     set_error("bsms_gmp_backward: workspace too small");
     return BSMS_EWORKSPACE;
   }
-  BSMS_CHECK_ARG(!g_deterministic || mode == BSMS_MODE_FP32,
-                 "bsms_gmp_backward: the deterministic option (bsms_set_deterministic) is served by BSMS_MODE_FP32 only");
+  BSMS_CHECK_ARG(!g_deterministic || mode != BSMS_MODE_FP16X3,
+                 "bsms_gmp_backward: the deterministic option (bsms_set_deterministic) is served by BSMS_MODE_FP32 and BSMS_MODE_BF16");
   if (mode == BSMS_MODE_BF16)
     return gmp_backward_tc(pl, w, x, pos, pos_batched, saved, g_out, g_x, gr, B, P, ws, ws_bytes, st);
   // fp32-parity tensor-core mode with the forward's node-level intermediates at hand: every GEMM on tcgen05

@@ -28,6 +28,7 @@ struct NodeBwdParams {
   float* G4;           // [rows,128] gradient of the first layer's activation (after its ReLU mask)
   float* gW[3];        // V2, V3, V4 gradients [128,128] (accumulated)
   float* gb[3];        // c2, c3, c4 gradients (accumulated)
+  float* part;         // deterministic option: per-CTA sums go to part[blockIdx.x][kDetNodeBwdStride] instead
   long long rows;
   int ntiles;
 };
@@ -249,7 +250,30 @@ __global__ void __launch_bounds__(256, 1) k_node_chain_bwd(const NodeBwdParams p
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  if (wacc) {
+  if (p.part) {
+    // deterministic option: plain stores of this CTA's sums (zeros when it had no tile); det_reduce adds them in order
+    float* part = p.part + (size_t)blockIdx.x * kDetNodeBwdStride;
+#pragma unroll 1
+    for (int l = 0; l < 3; ++l) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t rr_[32];
+        if (wacc) {
+          tmem_ld32(tmem_base + 128 * (l + 1) + lane_off + 64 * h + 32 * hh, rr_);
+          wait_ld();
+        } else {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) rr_[t] = 0u;
+        }
+        float* dst = part + l * 16384 + r * 128 + 64 * h + 32 * hh;
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4)
+          st4(dst + q4 * 4, make_float4(__uint_as_float(rr_[q4 * 4]), __uint_as_float(rr_[q4 * 4 + 1]),
+                                        __uint_as_float(rr_[q4 * 4 + 2]), __uint_as_float(rr_[q4 * 4 + 3])));
+      }
+      st4(part + 3 * 16384 + (l * 8 + warp) * 128 + 4 * lane, acc_b[l]);
+    }
+  } else if (wacc) {
 #pragma unroll 1
     for (int l = 0; l < 3; ++l) {
 #pragma unroll
@@ -280,7 +304,7 @@ __global__ void __launch_bounds__(256, 1) k_node_chain_bwd(const NodeBwdParams p
 // G4 = gradient of the first node layer's activation; accumulates dV2..dV4 and dc2..dc4.
 int node_chain_backward(const float* Yn, const float* g_out, const float* N1, const float* N2, const float* N3, int img,
                         const uint8_t* wpack_v2, float* G4, float* const* gW, float* const* gb, long long rows,
-                        cudaStream_t st) {
+                        cudaStream_t st, float* part) {
   if (rows == 0) return BSMS_OK;
   NodeBwdParams p;
   p.Yn = Yn;
@@ -295,6 +319,7 @@ int node_chain_backward(const float* Yn, const float* g_out, const float* N1, co
     p.gW[l] = gW[l];
     p.gb[l] = gb[l];
   }
+  p.part = part;
   p.rows = rows;
   p.ntiles = ceil_div(rows, 128);
   int dev = 0, sms = 148;
@@ -303,8 +328,17 @@ int node_chain_backward(const float* Yn, const float* g_out, const float* N1, co
   const size_t smem = 1024 + 6 * kWBlk + 3 * 8 + 16;
   BSMS_CUDA(cudaFuncSetAttribute(k_node_chain_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope ps_(PK_DGRAD, st);
-  k_node_chain_bwd<<<std::min(sms, p.ntiles), 256, smem, st>>>(p);
+  const int grid = std::min(sms, p.ntiles);
+  k_node_chain_bwd<<<grid, 256, smem, st>>>(p);
   BSMS_LAUNCHED();
+  if (part) {
+    DetSeg segs[6];
+    for (int l = 0; l < 3; ++l) {
+      segs[l] = DetSeg{gW[l], l * 16384, 0, grid, 1, 128, 128, 128, 128};
+      segs[3 + l] = DetSeg{gb[l], 3 * 16384 + l * 8 * 128, 0, grid, 8, 1, 128, 128, 128};
+    }
+    return det_reduce(part, kDetNodeBwdStride, segs, 6, st);
+  }
   return BSMS_OK;
 }
 

@@ -408,6 +408,7 @@ struct WgradBatch {
   WgradParams prob[6];
   int nprob;
   int ctas_per_prob;
+  float* part;  // deterministic option: per-CTA sums go to part[blockIdx.x][kDetWgradStride] instead of atomics
 };
 
 __device__ __forceinline__ uint32_t t_off(int r, int chunk) {
@@ -506,12 +507,24 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradBatch batch) {
     tmem_ld32(ta, r0);
     tmem_ld32(ta + 32, r1);
     wait_ld();
-    float* dst = p.dW + (size_t)n * p.ldo + 64 * hh;
+    if (batch.part) {
+      float* part = batch.part + (size_t)blockIdx.x * kDetWgradStride;
+      float* dst = part + n * 128 + 64 * hh;
 #pragma unroll
-    for (int t = 0; t < 32; ++t) atomicAdd(dst + t, __uint_as_float(r0[t]));
+      for (int t = 0; t < 32; t += 4)
+        st4(dst + t, make_float4(__uint_as_float(r0[t]), __uint_as_float(r0[t + 1]), __uint_as_float(r0[t + 2]), __uint_as_float(r0[t + 3])));
 #pragma unroll
-    for (int t = 0; t < 32; ++t) atomicAdd(dst + 32 + t, __uint_as_float(r1[t]));
-    if (p.db) atomicAdd(p.db + cc, acc_b);
+      for (int t = 0; t < 32; t += 4)
+        st4(dst + 32 + t, make_float4(__uint_as_float(r1[t]), __uint_as_float(r1[t + 1]), __uint_as_float(r1[t + 2]), __uint_as_float(r1[t + 3])));
+      part[16384 + rh * 128 + cc] = acc_b;
+    } else {
+      float* dst = p.dW + (size_t)n * p.ldo + 64 * hh;
+#pragma unroll
+      for (int t = 0; t < 32; ++t) atomicAdd(dst + t, __uint_as_float(r0[t]));
+#pragma unroll
+      for (int t = 0; t < 32; ++t) atomicAdd(dst + 32 + t, __uint_as_float(r1[t]));
+      if (p.db) atomicAdd(p.db + cc, acc_b);
+    }
   }
   fence_before_sync();
   __syncthreads();
@@ -799,10 +812,11 @@ int wgrad_tc_split_batch(const WgradParams* probs, int nprob, const unsigned* g_
 }
 
 // One launch for up to 6 weight-gradient problems over the same number of rows.
-int wgrad_tc_batch(const WgradParams* probs, int nprob, cudaStream_t st) {
+int wgrad_tc_batch(const WgradParams* probs, int nprob, cudaStream_t st, float* part) {
   if (nprob == 0 || probs[0].rows == 0) return BSMS_OK;
   WgradBatch b;
   b.nprob = nprob;
+  b.part = part;
   const int ntiles = ceil_div(probs[0].rows, 128);
   for (int i = 0; i < nprob; ++i) {
     b.prob[i] = probs[i];
@@ -814,6 +828,15 @@ int wgrad_tc_batch(const WgradParams* probs, int nprob, cudaStream_t st) {
   ProfScope ps_(PK_WGRAD, st);
   k_wgrad_tc<<<b.ctas_per_prob * nprob, 256, smem, st>>>(b);
   BSMS_LAUNCHED();
+  if (part) {
+    DetSeg segs[12];
+    int ns = 0;
+    for (int i = 0; i < nprob; ++i) {
+      segs[ns++] = DetSeg{probs[i].dW, 0, i * b.ctas_per_prob, b.ctas_per_prob, 1, 128, 128, 128, probs[i].ldo};
+      if (probs[i].db) segs[ns++] = DetSeg{probs[i].db, 16384, i * b.ctas_per_prob, b.ctas_per_prob, 2, 1, 128, 128, 128};
+    }
+    return det_reduce(part, kDetWgradStride, segs, ns, st);
+  }
   return BSMS_OK;
 }
 
@@ -834,7 +857,7 @@ WgradParams wgrad_problem(const float* G, int ldg, const float* X, int ldx, floa
 int wgrad_tc(const float* G, int ldg, const float* X, int ldx, float* dW, int ldo, float* db, long long rows,
              cudaStream_t st) {
   WgradParams p = wgrad_problem(G, ldg, X, ldx, dW, ldo, db, rows);
-  return wgrad_tc_batch(&p, 1, st);
+  return wgrad_tc_batch(&p, 1, st, nullptr);
 }
 
 // Test hook: Y = ((X W^T) or (X W)) [. (mask > 0)] on the split-operand tensor-core layer; a_is_grad: scale X from its

@@ -42,9 +42,11 @@ def set_default_mode(mode: str):
 
 def set_deterministic(on: bool):
     """Bitwise run-to-run reproducible forward and backward (the role torch.use_deterministic_algorithms plays for the
-    reference, whose scatter_add_ is order-dependent on CUDA).  While on, every GMP block runs the exact-fp32 kernels
-    — CSR segment sums in row order, no atomics — with ordered weight-gradient commits (bsms_set_deterministic),
-    whatever mode it was built with; the transfer operators are order-fixed in every mode.  About 9x slower than bf16."""
+    reference, whose scatter_add_ is order-dependent on CUDA).  While on: `bf16` blocks keep their tensor-core kernels,
+    but the fused edge kernels hand their per-edge-row results to order-fixed CSR segment sums instead of reducing with
+    red.add, and every per-CTA atomic flush becomes a partial-sum block + one ordered reduction (about 1.5x the bf16
+    step); `fp32` blocks commit their weight-gradient partial sums in ticket order; `fp16x3` blocks run as `fp32`
+    (same 1e-5 grade).  The transfer operators are order-fixed CSR sums in every mode."""
     lib.bsms_set_deterministic(1 if on else 0)
 
 
@@ -180,7 +182,8 @@ class GMP(nn.Module):
             raise RuntimeError("pos and x disagree on the batch size")
         pos = pos.detach().to(torch.float32).contiguous()
         skip3 = None if skip is None else _as_b3(skip, "skip")
-        if lib.bsms_get_deterministic():
+        if lib.bsms_get_deterministic() and self.mode == _lib.MODE_FP16X3:
+            # the fp32-parity mode's deterministic form is the exact-fp32 mode (same 1e-5 grade, ordered reductions)
             out = _GMPFunction.apply(x3, pos, skip3, level, _lib.MODE_FP32, self.pos_dim, None, *self._params())
         else:
             out = _GMPFunction.apply(x3, pos, skip3, level, self.mode, self.pos_dim, self._packed_weights(), *self._params())

@@ -324,11 +324,16 @@ void bsms_hierarchy_free_host(void* handle);
 int bsms_debug_lin_split(const float* X, int64_t rows, const float* W, int32_t b_mn, const float* mask,
                          int32_t a_is_grad, float* Y, void* scratch, void* stream);
 
-/* Deterministic option (process-wide switch, default off): bitwise run-to-run reproducible results.  Served by
- * BSMS_MODE_FP32 — its segment sums walk CSR rows in order without atomics, and with the switch on its
- * split-over-rows weight-gradient kernels commit their partial sums in a fixed (ticket) order.  While the switch is on,
- * bsms_gmp_forward / bsms_gmp_backward in a tensor-core mode return BSMS_EINVAL (those modes reduce with red.add in
- * arrival order); the transfer operators are order-fixed CSR sums in every mode.  The reference offers
+/* Deterministic option (process-wide switch, default off): bitwise run-to-run reproducible results.
+ *  - BSMS_MODE_FP32: segment sums walk CSR rows in order without atomics; with the switch on the split-over-rows
+ *    weight-gradient kernels commit their partial sums in a fixed (ticket) order.
+ *  - BSMS_MODE_BF16: the fused tcgen05 edge kernels write their per-edge-row results as [B*E,128] rows and order-fixed
+ *    CSR segment sums replace the red.add reductions into node rows; every per-CTA atomic flush of a weight / bias
+ *    gradient becomes a per-CTA partial-sum block + one ordered reduction (bsms_gmp_workspace_bytes grows accordingly —
+ *    set the switch BEFORE sizing workspaces).
+ *  - BSMS_MODE_FP16X3: bsms_gmp_forward / bsms_gmp_backward return BSMS_EINVAL while the switch is on (use
+ *    BSMS_MODE_FP32, the same 1e-5 grade).
+ * The transfer operators are order-fixed CSR sums in every mode.  The reference offers
  * torch.use_deterministic_algorithms for the same purpose (its scatter_add_ is otherwise order-dependent on CUDA,
  * src/utils/basic.py:287-343). */
 void bsms_set_deterministic(int32_t on);

@@ -1,7 +1,8 @@
 """The deterministic option (ops.set_deterministic / bsms_set_deterministic): forward, data gradient and every parameter
-gradient of the whole processor are BITWISE identical from run to run, and still within the fp32 tolerances of the
-reference golden.  The tensor-core modes reduce with red.add in arrival order and must refuse to run under the switch
-at the C-ABI (the Python host routes every block to the exact-fp32 kernels instead)."""
+gradient of the whole processor are BITWISE identical from run to run — in the default mode (routed to the exact-fp32
+kernels with ordered commits, still within the fp32 tolerances of the reference golden) and in the bf16 mode (tensor-core
+kernels with rows + CSR-ordered segment sums and per-CTA partial-sum blocks, still within the bf16 tolerances).  The
+fp16x3 kernels reduce with red.add in arrival order and must refuse to run under the switch at the C-ABI."""
 import pytest
 import torch
 
@@ -48,9 +49,45 @@ def test_deterministic_option_is_bitwise_reproducible(case, hname):
         x3 = (h if h.dim() == 3 else h.unsqueeze(0)).contiguous()
         lp = P.level_plan(gs[0], x3.shape[1])
         with pytest.raises(_lib.BsmsError):
-            ops._GMPFunction.apply(x3, ps.contiguous(), None, lp, _lib.MODE_BF16, blk.pos_dim, None, *blk._params())
+            ops._GMPFunction.apply(x3, ps.contiguous(), None, lp, _lib.MODE_FP16X3, blk.pos_dim, None, *blk._params())
     finally:
         ops.set_deterministic(False)
     # informational: how far two default-mode runs are apart
     a, b = _step(model, h, ids, gs, ps), _step(model, h, ids, gs, ps)
     print(f"\n[{case}] default mode run-to-run max-rel: out {max_rel(a[0], b[0]):.1e}, grad_h {max_rel(a[1], b[1]):.1e}")
+
+
+@pytest.mark.parametrize("case,hname", [("grid44", "grid44"), ("grid72", "grid72"), ("ico3", "ico3")])
+def test_deterministic_bf16_is_bitwise_reproducible(case, hname):
+    """bf16 under the switch: tensor-core kernels, bitwise identical run to run, and the same function as the default
+    bf16 path up to summation order (a different order moves single values across bf16 rounding boundaries of the next
+    GEMM's operands, so two default runs differ at the same level: forward 5e-3 max-rel, gradients 2e-2 L2-relative),
+    forward within the bf16 bound of the reference golden."""
+    from bsms_gnn_b200 import ops
+    from tests.util import l2_rel
+    dev = torch.device("cuda:0")
+    rec = load_npz(f"bsgmp_{case}.npz")
+    m_gs, m_ids, pos, d = load_hier(hname)
+    h, ps = bsgmp_inputs(rec, pos, pos.shape[0])
+    model = ops.BSGMP(d, 128, 3, int(rec["P"]), mode="bf16").to(dev)
+    model.load_state_dict(O.init_params(d, pos_dim=int(rec["P"]), seed=int(rec["seed"])))
+    h, ps = h.to(dev), ps.to(dev)
+    ids, gs = [i.to(dev) for i in m_ids], [g.to(dev) for g in m_gs]
+    base = _step(model, h, ids, gs, ps)
+    ops.set_deterministic(True)
+    try:
+        runs = [_step(model, h, ids, gs, ps) for _ in range(4)]
+        with torch.no_grad():
+            inf = model(h, ids, gs, ps)  # inference path (no saved tensors, packed-weight cache)
+    finally:
+        ops.set_deterministic(False)
+    for k, r in enumerate(runs[1:]):
+        for i, (a, b) in enumerate(zip(runs[0], r)):
+            assert torch.equal(a, b), f"run {k + 1}, tensor {i}: max diff {float((a - b).abs().max()):.3e}"
+    assert torch.equal(inf, runs[0][0])
+    rs = int(rec["row_stride"])
+    assert max_rel(runs[0][0].cpu()[..., ::rs, :], rec["out"]) < 3e-2
+    assert max_rel(runs[0][0], base[0]) < 5e-3
+    worst = max(l2_rel(a, b) for a, b in zip(runs[0][1:], base[1:]))
+    print(f"\n[{case}] deterministic bf16 vs default bf16: out {max_rel(runs[0][0], base[0]):.1e}, worst gradient L2-rel {worst:.1e}")
+    assert worst < 2e-2
