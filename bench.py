@@ -865,6 +865,35 @@ def main():
         del model_p, params_p
         torch.cuda.empty_cache()
 
+    # ---- N = 1: the same step under the deterministic option (ops.set_deterministic): tensor-core kernels with
+    #      rows + CSR-ordered segment sums and ordered partial-sum reductions; two steps must agree bit for bit
+    det_mode = None
+    if world == 1 and args.mode == "bf16" and os.environ.get("BSMS_BENCH_DET_MODE", "1") != "0":
+        from bsms_gnn_b200 import ops as _ops
+        _ops.set_deterministic(True)
+        try:
+            for _ in range(3):
+                step(h_dev, pos_dev)
+            g1 = [q.grad.clone() for q in params]
+            step(h_dev, pos_dev)
+            same = all(torch.equal(a_, q.grad) for a_, q in zip(g1, params))
+            torch.cuda.synchronize()
+            ed0, ed1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ed0.record()
+            for _ in range(5):
+                step(h_dev, pos_dev)
+            ed1.record()
+            torch.cuda.synchronize()
+            ms_d = ed0.elapsed_time(ed1) / 5
+        finally:
+            _ops.set_deterministic(False)
+        det_mode = {"mode": args.mode, "ms_per_step": ms_d, "value": B * E0 / (ms_d * 1e-3) / 1e6, "unit": "M-edges/s",
+                    "bitwise_equal_steps": bool(same), "steps": 5, "warmup": 4,
+                    "note": "bsms_set_deterministic(1): same workload, every parameter gradient of two consecutive steps compared bit for bit"}
+        assert same, "deterministic option: two steps differ"
+        del g1
+        torch.cuda.empty_cache()
+
     # ---- N = 1: BASELINE.json configs 2 and 4 (whole-model rollouts, B = 1) in the same run, short form
     rollouts = None
     if world == 1 and os.environ.get("BSMS_BENCH_ROLLOUT", "1") != "0":
@@ -900,7 +929,8 @@ def main():
                             "(the rollout configs in extra.rollouts return every state to the host)"},
             "gpu_launches": int(launches),
             "roofline": roofline, "roofline_fused_edge_kernel": roofline_edge, "kernel_breakdown": breakdown, "cpu_baseline": cpu,
-            "self_check": self_check, "extra": {"mesh_strong": mesh_strong, "rollouts": rollouts, "parity_mode": parity_mode},
+            "self_check": self_check, "extra": {"mesh_strong": mesh_strong, "rollouts": rollouts, "parity_mode": parity_mode,
+                                                      "deterministic_mode": det_mode},
         }
         print(json.dumps(out), flush=True)
     if world > 1:
