@@ -14,6 +14,8 @@
 // The loads of the next operand tile are issued in the shadow of the current MMA batch.  The three
 // weight-gradient accumulators stay in TMEM for the whole persistent loop (as in edge_chain_bwd.cu);
 // bias gradients are column sums of the staged gradient tiles.
+#include <stdlib.h>
+
 #include "chain.cuh"
 
 namespace bsms {
@@ -29,6 +31,7 @@ struct NodeBwdParams {
   float* gW[3];        // V2, V3, V4 gradients [128,128] (accumulated)
   float* gb[3];        // c2, c3, c4 gradients (accumulated)
   float* part;         // deterministic option: per-CTA sums go to part[blockIdx.x][kDetNodeBwdStride] instead
+  int l2_prefetch;     // request the next tile's rows / images into L2 under the first MMA batch of the current tile
   long long rows;
   int ntiles;
 };
@@ -199,6 +202,26 @@ __global__ void __launch_bounds__(256, 1) k_node_chain_bwd(const NodeBwdParams p
     }
     sync_all();
     issue_pair(tmem_base + 384, aTG, aT3, aV[2]);  // dV4 += G1^T N3 ; D = G1 V4
+    if (p.l2_prefetch && tile + (int)gridDim.x < p.ntiles) {
+      // the next tile's rows are requested into L2 now (fire and forget): its three dependent load phases then see
+      // L2 latency instead of DRAM latency.  128 rows x 4 lines x 3 tensors (+ 2 x 256 lines of images) over 256 threads
+      const long long nrow0 = (long long)(tile + gridDim.x) * 128;
+      const long long lim = p.rows * kD;  // floats
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const long long off = nrow0 * kD + (long long)(tid + 256 * k) * 32;  // 32 floats = one 128-byte line
+        if (off < lim) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.Yn + off));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.g_out + off));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.N[0] + off));
+        }
+      }
+      if (p.img) {
+        const size_t ioff = (size_t)(tile + gridDim.x) * kWBlk + (size_t)tid * 128;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(p.N[2]) + ioff));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(p.N[1]) + ioff));
+      }
+    }
     colsum(s_TG, acc_b[2]);
     if (!p.img) load_tile(p.N[1], row0, s_T2);     // N2 -> T2 in the shadow of the MMAs
     wait_mma();
@@ -320,6 +343,8 @@ int node_chain_backward(const float* Yn, const float* g_out, const float* N1, co
     p.gb[l] = gb[l];
   }
   p.part = part;
+  static const int l2pf = getenv("BSMS_NODE_PF") ? atoi(getenv("BSMS_NODE_PF")) : 0;  // experiment switch
+  p.l2_prefetch = l2pf;
   p.rows = rows;
   p.ntiles = ceil_div(rows, 128);
   int dev = 0, sms = 148;
