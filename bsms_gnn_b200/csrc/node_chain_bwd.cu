@@ -14,6 +14,7 @@
 // The loads of the next operand tile are issued in the shadow of the current MMA batch.  The three
 // weight-gradient accumulators stay in TMEM for the whole persistent loop (as in edge_chain_bwd.cu);
 // bias gradients are column sums of the staged gradient tiles.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "chain.cuh"
@@ -32,6 +33,7 @@ struct NodeBwdParams {
   float* gb[3];        // c2, c3, c4 gradients (accumulated)
   float* part;         // deterministic option: per-CTA sums go to part[blockIdx.x][kDetNodeBwdStride] instead
   int l2_prefetch;     // request the next tile's rows / images into L2 under the first MMA batch of the current tile
+  unsigned long long* prof;  // optional [16] per-phase cycle sums of thread 0 of every CTA (BSMS_PHASE_PROF=1)
   long long rows;
   int ntiles;
 };
@@ -160,6 +162,15 @@ __global__ void __launch_bounds__(256, 1) k_node_chain_bwd(const NodeBwdParams p
     }
   };
 
+  long long tprev = p.prof ? clock64() : 0;
+  unsigned long long cyc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  auto mark = [&](int k) {
+    if (p.prof && tid == 0) {
+      const long long t = clock64();
+      cyc[k] += (unsigned long long)(t - tprev);
+      tprev = t;
+    }
+  };
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const long long row0 = (long long)tile * 128;
     if (p.img && tid == 0) {
@@ -194,6 +205,7 @@ __global__ void __launch_bounds__(256, 1) k_node_chain_bwd(const NodeBwdParams p
         }
       }
     }
+    mark(0);
     if (p.img) {
       mbar_wait(bar_l, phase_l);  // the two image tiles have landed
       phase_l ^= 1;
@@ -201,6 +213,7 @@ __global__ void __launch_bounds__(256, 1) k_node_chain_bwd(const NodeBwdParams p
       load_tile(p.N[2], row0, s_T3);
     }
     sync_all();
+    mark(1);
     issue_pair(tmem_base + 384, aTG, aT3, aV[2]);  // dV4 += G1^T N3 ; D = G1 V4
     if (p.l2_prefetch && tile + (int)gridDim.x < p.ntiles) {
       // the next tile's rows are requested into L2 now (fire and forget): its three dependent load phases then see
@@ -225,19 +238,24 @@ __global__ void __launch_bounds__(256, 1) k_node_chain_bwd(const NodeBwdParams p
     colsum(s_TG, acc_b[2]);
     if (!p.img) load_tile(p.N[1], row0, s_T2);     // N2 -> T2 in the shadow of the MMAs
     wait_mma();
+    mark(2);
     grad_epilogue(s_T3);                           // G2 -> T3
     sync_all();
+    mark(3);
     issue_pair(tmem_base + 256, aT3, aT2, aV[1]);  // dV3 += G2^T N2 ; D = G2 V3
     colsum(s_T3, acc_b[1]);
     load_tile(p.N[0], row0, s_TG);                 // N1 -> TG (G1 is dead: its MMAs completed)
     wait_mma();
+    mark(4);
     grad_epilogue(s_T2);                           // G3 -> T2
     sync_all();
+    mark(5);
     issue_pair(tmem_base + 128, aT2, aTG, aV[0]);  // dV2 += G3^T N1 ; D = G3 V2
     wacc = 1;
     colsum(s_T2, acc_b[0]);
     wait_mma();
     __syncthreads();  // every warp is done with the column sums over T2 before the staging overwrites it
+    mark(6);
     // ---- G4 = D . [N1 > 0] -> fp32 staging over T3|T2 (16-byte chunks XOR-swizzled by row)
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
@@ -260,6 +278,7 @@ __global__ void __launch_bounds__(256, 1) k_node_chain_bwd(const NodeBwdParams p
       }
     }
     __syncthreads();
+    mark(7);
 #pragma unroll 4
     for (int rr = warp * 16; rr < warp * 16 + 16; ++rr) {
       const long long row = row0 + rr;
@@ -267,7 +286,10 @@ __global__ void __launch_bounds__(256, 1) k_node_chain_bwd(const NodeBwdParams p
         st4(p.G4 + row * kD + 4 * lane, *reinterpret_cast<const float4*>(s_stage + rr * 128 + ((lane ^ (rr & 31)) << 2)));
     }
     sync_all();  // the tiles are rewritten by the next tile (by cp.async.bulk in image mode: proxy fence included)
+    mark(8);
   }
+  if (p.prof && tid == 0)
+    for (int k = 0; k < 9; ++k) atomicAdd(p.prof + k, cyc[k]);
 
   // ---- flush: weight-gradient accumulators (TMEM) and the per-lane bias partial sums
   fence_before_sync();
@@ -354,8 +376,25 @@ int node_chain_backward(const float* Yn, const float* g_out, const float* N1, co
   BSMS_CUDA(cudaFuncSetAttribute(k_node_chain_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope ps_(PK_DGRAD, st);
   const int grid = std::min(sms, p.ntiles);
+  static const bool phase_prof = getenv("BSMS_PHASE_PROF") != nullptr;
+  static unsigned long long* d_prof = nullptr;
+  p.prof = nullptr;
+  if (phase_prof) {
+    if (!d_prof) BSMS_CUDA(cudaMalloc(&d_prof, 16 * sizeof(unsigned long long)));
+    BSMS_CUDA(cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), st));
+    p.prof = d_prof;
+  }
   k_node_chain_bwd<<<grid, 256, smem, st>>>(p);
   BSMS_LAUNCHED();
+  if (phase_prof) {  // debug aid: per-phase cycles per tile: 0 LN backward (loads + math), 1 wait N3/N2 images, 2 MMA pair 1 +
+                     // column sums, 3 epilogue 1, 4 MMA pair 2 + N1 rows, 5 epilogue 2, 6 MMA pair 3, 7 staging, 8 row stores
+    unsigned long long h[16];
+    BSMS_CUDA(cudaMemcpyAsync(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost, st));
+    BSMS_CUDA(cudaStreamSynchronize(st));
+    fprintf(stderr, "[node bwd phases] tiles %d:", p.ntiles);
+    for (int k = 0; k < 9; ++k) fprintf(stderr, " %llu", h[k] / (unsigned long long)p.ntiles);
+    fprintf(stderr, "\n");
+  }
   if (part) {
     DetSeg segs[6];
     for (int l = 0; l < 3; ++l) {
