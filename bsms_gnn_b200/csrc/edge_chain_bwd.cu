@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
     for (int blk = 0; blk < 3; ++blk) bulk_g2s(aW[blk], p.wpack + (size_t)blk * kWBlk, kWBlk, bar_w);
     mbar_wait(bar_w, 0);
   }
+  __syncwarp();  // lane 0 rejoins its warp (a warp left split runs its collectives on the slow path until the next barrier)
   const uint32_t d_tmem = tmem_base;  // D: cols [0,128); dW2/dW3/dW4: cols [128,256), [256,384), [384,512)
   const uint32_t lane_off = (uint32_t)(q * 32) << 16;
   // this thread's two groups of 32 channels (= TMEM columns of D): NS: one group in each N half

@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(256, 1) k_node_chain_bwd(const NodeBwdParams p
     for (int blk = 0; blk < 3; ++blk) bulk_g2s(aV[blk], p.wpack + (size_t)blk * kWBlk, kWBlk, bar_w);
     mbar_wait(bar_w, 0);
   }
+  __syncwarp();  // lane 0 rejoins its warp here: a warp that stays split runs every collective on its slow path
   const uint32_t d_tmem = tmem_base;  // D: cols [0,128); dV2/dV3/dV4: cols [128,256), [256,384), [384,512)
   const uint32_t lane_off = (uint32_t)(q * 32) << 16;
   const uint32_t d_mine = d_tmem + lane_off + 64 * h;
@@ -179,11 +180,12 @@ __global__ void __launch_bounds__(256, 1) k_node_chain_bwd(const NodeBwdParams p
       bulk_g2s(aT3, reinterpret_cast<const uint8_t*>(p.N[2]) + (size_t)tile * kWBlk, kWBlk, bar_l);
       bulk_g2s(aT2, reinterpret_cast<const uint8_t*>(p.N[1]) + (size_t)tile * kWBlk, kWBlk, bar_l);
     }
+    __syncwarp();
     // ---- G1 = LayerNorm backward of g_out through Yn (warp per row), N3 -> T3
     {
       const uint32_t col_off = (uint32_t)((lane >> 4) * 16384 + (lane & 1) * 8);
       const int chunk7 = (lane >> 1) & 7;
-#pragma unroll
+#pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         float4 y[8], g[8];
         coop_rows_load<8>(p.Yn, kD, row0, p.rows, warp * 16 + 8 * half, lane, y);
@@ -191,20 +193,36 @@ __global__ void __launch_bounds__(256, 1) k_node_chain_bwd(const NodeBwdParams p
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int rr = warp * 16 + 8 * half + u;
-          const float mean = warp_sum(y[u].x + y[u].y + y[u].z + y[u].w) * (1.f / 128.f);
-          const float dx = y[u].x - mean, dy = y[u].y - mean, dz = y[u].z - mean, dw = y[u].w - mean;
-          const float var = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.f / 128.f);
+          // one pass: sums of d = y - shift, d^2, g and g d travel through ONE butterfly (four independent values per
+          // step instead of three dependent reductions of 5 steps each); the shift (the row's first element) keeps
+          // E[d^2] - E[d]^2 free of cancellation, as in the forward kernels
+          const float shift = __shfl_sync(0xffffffffu, y[u].x, 0);
+          const float dx = y[u].x - shift, dy = y[u].y - shift, dz = y[u].z - shift, dw = y[u].w - shift;
+          float s1 = (dx + dy) + (dz + dw);
+          float s2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
+          float s3 = (g[u].x + g[u].y) + (g[u].z + g[u].w);
+          float s4 = fmaf(g[u].x, dx, fmaf(g[u].y, dy, fmaf(g[u].z, dz, g[u].w * dw)));
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float t1 = __shfl_xor_sync(0xffffffffu, s1, o), t2 = __shfl_xor_sync(0xffffffffu, s2, o);
+            const float t3 = __shfl_xor_sync(0xffffffffu, s3, o), t4 = __shfl_xor_sync(0xffffffffu, s4, o);
+            s1 += t1; s2 += t2; s3 += t3; s4 += t4;
+          }
+          const float md = s1 * (1.f / 128.f);
+          const float var = fmaxf(s2 * (1.f / 128.f) - md * md, 0.f);
           const float rstd = 1.f / sqrtf(var + 1e-5f);
-          const float hx = dx * rstd, hy = dy * rstd, hz = dz * rstd, hw_ = dw * rstd;
-          const float c1 = warp_sum(g[u].x + g[u].y + g[u].z + g[u].w) * (1.f / 128.f);
-          const float c2 = warp_sum(g[u].x * hx + g[u].y * hy + g[u].z * hz + g[u].w * hw_) * (1.f / 128.f);
+          const float c1 = s3 * (1.f / 128.f);
+          const float c2 = rstd * (s4 * (1.f / 128.f) - md * c1);  // mean over the row of g h, h = (d - md) rstd
+          const float hx = (dx - md) * rstd, hy = (dy - md) * rstd, hz = (dz - md) * rstd, hw_ = (dw - md) * rstd;
           uint2 pk;  // rows past the end load zeros: y = g = 0 gives G1 = 0
           pk.x = pack_bf16(rstd * (g[u].x - c1 - hx * c2), rstd * (g[u].y - c1 - hy * c2));
           pk.y = pack_bf16(rstd * (g[u].z - c1 - hz * c2), rstd * (g[u].w - c1 - hw_ * c2));
           *reinterpret_cast<uint2*>(s_TG + col_off + rr * 128 + ((chunk7 ^ (rr & 7)) << 4)) = pk;
         }
+
       }
     }
+    if (p.prof && tid == 0 && tile == (int)blockIdx.x) cyc[9] = (unsigned long long)(clock64() - tprev);
     mark(0);
     if (p.img) {
       mbar_wait(bar_l, phase_l);  // the two image tiles have landed
@@ -289,7 +307,7 @@ __global__ void __launch_bounds__(256, 1) k_node_chain_bwd(const NodeBwdParams p
     mark(8);
   }
   if (p.prof && tid == 0)
-    for (int k = 0; k < 9; ++k) atomicAdd(p.prof + k, cyc[k]);
+    for (int k = 0; k < 10; ++k) atomicAdd(p.prof + k, cyc[k]);
 
   // ---- flush: weight-gradient accumulators (TMEM) and the per-lane bias partial sums
   fence_before_sync();
@@ -393,6 +411,7 @@ int node_chain_backward(const float* Yn, const float* g_out, const float* N1, co
     BSMS_CUDA(cudaStreamSynchronize(st));
     fprintf(stderr, "[node bwd phases] tiles %d:", p.ntiles);
     for (int k = 0; k < 9; ++k) fprintf(stderr, " %llu", h[k] / (unsigned long long)p.ntiles);
+    fprintf(stderr, " | phase 0 of a CTA's first tile: %llu", h[9] / (unsigned long long)grid);
     fprintf(stderr, "\n");
   }
   if (part) {

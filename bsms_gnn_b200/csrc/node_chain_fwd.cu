@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(256, 1) k_node_chain_fwd(const NodeFwdParams p
     for (int blk = 0; blk < 3; ++blk) bulk_g2s(aV[blk], p.wpack + (size_t)blk * kWBlk, kWBlk, bar_w);
     mbar_wait(bar_w, 0);
   }
+  __syncwarp();  // lane 0 rejoins its warp (a warp left split runs its collectives on the slow path until the next barrier)
   const uint32_t lane_off = (uint32_t)(q * 32) << 16;
   const uint32_t d_mine = d_tmem + lane_off + 64 * h;
   uint32_t phase = 0;

@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(128, 2) k_lin(const LinParams p) {
         bulk_g2s(sbase + (nb * p.KB + kb) * BLK, p.wblk[nb * 2 + kb], BLK, bar_w);
     mbar_wait(bar_w, 0);
   }
+  __syncwarp();  // lane 0 rejoins its warp (a warp left split runs its collectives on the slow path until the next barrier)
   const uint32_t d_tmem = tmem_base;       // 128 columns
   const uint32_t a_tmem = tmem_base + 128;  // 64 (hi) [+ 64 (lo)]
   const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
