@@ -190,34 +190,55 @@ __global__ void __launch_bounds__(256, 1) k_node_chain_bwd(const NodeBwdParams p
         float4 y[8], g[8];
         coop_rows_load<8>(p.Yn, kD, row0, p.rows, warp * 16 + 8 * half, lane, y);
         coop_rows_load<8>(p.g_out, kD, row0, p.rows, warp * 16 + 8 * half, lane, g);
+        // One pass over FOUR rows at a time: the sums of d = y - shift, d^2, g and g d of the four rows travel through
+        // one butterfly — 16 independent shuffles per step, issued back to back, instead of a dependent chain of
+        // 5-step reductions per row (the phase was bound by shuffle latency: ~580 cycles per row); the shift (the row's
+        // first element) keeps E[d^2] - E[d]^2 free of cancellation, as in the forward kernels
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int rr = warp * 16 + 8 * half + u;
-          // one pass: sums of d = y - shift, d^2, g and g d travel through ONE butterfly (four independent values per
-          // step instead of three dependent reductions of 5 steps each); the shift (the row's first element) keeps
-          // E[d^2] - E[d]^2 free of cancellation, as in the forward kernels
-          const float shift = __shfl_sync(0xffffffffu, y[u].x, 0);
-          const float dx = y[u].x - shift, dy = y[u].y - shift, dz = y[u].z - shift, dw = y[u].w - shift;
-          float s1 = (dx + dy) + (dz + dw);
-          float s2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
-          float s3 = (g[u].x + g[u].y) + (g[u].z + g[u].w);
-          float s4 = fmaf(g[u].x, dx, fmaf(g[u].y, dy, fmaf(g[u].z, dz, g[u].w * dw)));
+        for (int u0 = 0; u0 < 8; u0 += 4) {
+          float sh[4], s1[4], s2[4], s3[4], s4[4];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) sh[v] = __shfl_sync(0xffffffffu, y[u0 + v].x, 0);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const float4 yy = y[u0 + v], gg = g[u0 + v];
+            const float dx = yy.x - sh[v], dy = yy.y - sh[v], dz = yy.z - sh[v], dw = yy.w - sh[v];
+            s1[v] = (dx + dy) + (dz + dw);
+            s2[v] = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
+            s3[v] = (gg.x + gg.y) + (gg.z + gg.w);
+            s4[v] = fmaf(gg.x, dx, fmaf(gg.y, dy, fmaf(gg.z, dz, gg.w * dw)));
+          }
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
-            const float t1 = __shfl_xor_sync(0xffffffffu, s1, o), t2 = __shfl_xor_sync(0xffffffffu, s2, o);
-            const float t3 = __shfl_xor_sync(0xffffffffu, s3, o), t4 = __shfl_xor_sync(0xffffffffu, s4, o);
-            s1 += t1; s2 += t2; s3 += t3; s4 += t4;
+            float t1[4], t2[4], t3[4], t4[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              t1[v] = __shfl_xor_sync(0xffffffffu, s1[v], o);
+              t2[v] = __shfl_xor_sync(0xffffffffu, s2[v], o);
+              t3[v] = __shfl_xor_sync(0xffffffffu, s3[v], o);
+              t4[v] = __shfl_xor_sync(0xffffffffu, s4[v], o);
+            }
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              s1[v] += t1[v]; s2[v] += t2[v]; s3[v] += t3[v]; s4[v] += t4[v];
+            }
           }
-          const float md = s1 * (1.f / 128.f);
-          const float var = fmaxf(s2 * (1.f / 128.f) - md * md, 0.f);
-          const float rstd = 1.f / sqrtf(var + 1e-5f);
-          const float c1 = s3 * (1.f / 128.f);
-          const float c2 = rstd * (s4 * (1.f / 128.f) - md * c1);  // mean over the row of g h, h = (d - md) rstd
-          const float hx = (dx - md) * rstd, hy = (dy - md) * rstd, hz = (dz - md) * rstd, hw_ = (dw - md) * rstd;
-          uint2 pk;  // rows past the end load zeros: y = g = 0 gives G1 = 0
-          pk.x = pack_bf16(rstd * (g[u].x - c1 - hx * c2), rstd * (g[u].y - c1 - hy * c2));
-          pk.y = pack_bf16(rstd * (g[u].z - c1 - hz * c2), rstd * (g[u].w - c1 - hw_ * c2));
-          *reinterpret_cast<uint2*>(s_TG + col_off + rr * 128 + ((chunk7 ^ (rr & 7)) << 4)) = pk;
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const int rr = warp * 16 + 8 * half + u0 + v;
+            const float4 yy = y[u0 + v], gg = g[u0 + v];
+            const float md = s1[v] * (1.f / 128.f);
+            const float var = fmaxf(s2[v] * (1.f / 128.f) - md * md, 0.f);
+            const float rstd = 1.f / sqrtf(var + 1e-5f);
+            const float c1 = s3[v] * (1.f / 128.f);
+            const float c2 = rstd * (s4[v] * (1.f / 128.f) - md * c1);  // mean over the row of g h, h = (d - md) rstd
+            const float m = sh[v] + md;
+            const float hx = (yy.x - m) * rstd, hy = (yy.y - m) * rstd, hz = (yy.z - m) * rstd, hw_ = (yy.w - m) * rstd;
+            uint2 pk;  // rows past the end load zeros: y = g = 0 gives G1 = 0
+            pk.x = pack_bf16(rstd * (gg.x - c1 - hx * c2), rstd * (gg.y - c1 - hy * c2));
+            pk.y = pack_bf16(rstd * (gg.z - c1 - hz * c2), rstd * (gg.w - c1 - hw_ * c2));
+            *reinterpret_cast<uint2*>(s_TG + col_off + rr * 128 + ((chunk7 ^ (rr & 7)) << 4)) = pk;
+          }
         }
 
       }
