@@ -76,7 +76,7 @@ __device__ __forceinline__ float4 make_fiber(const float* __restrict__ pb, int P
   return P == 1 ? make_float4(d0, nrm, 0.f, 0.f) : (P == 2 ? make_float4(d0, d1, nrm, 0.f) : make_float4(d0, d1, d2, nrm));
 }
 
-// Structure notes (measured on B200, profiles/r2_bwd_*.txt):
+// Structure notes (measured on B200, profiles/r2_phase_cycles.txt, profiles/r2_edge_kernels_ncu.txt):
 //  * ReLU + bf16 packing is one cvt (F2FP.RELU), ReLU masks are re-derived from the stored activation tiles
 //    (a > 0 <=> its bf16 image is non-zero), LayerNorm backward is two FMAs per element, and the
 //    weight-gradient MMA of every backward layer is issued AFTER its data-gradient MMA on its own barrier,
