@@ -137,3 +137,27 @@ def test_native_views_outlive_the_call():
     junk = [np.zeros(1 << 20, dtype=np.int64) for _ in range(8)]  # churn the allocator
     assert np.array_equal(last_g, want[0][-1]) and np.array_equal(last_i, want[1][0])
     del junk
+
+
+def test_reference_graph_selfcheck_clusters():
+    """The reference's own `Graph` self-check (src/graph_wrappers/graph_wrapper.py:216-241): two directed 3-cycles on six
+    nodes form the clusters [[0, 1, 2], [3, 4, 5]] — through the library's host code; then one bi-stride level of all
+    three builders on it: from the seed a directed 3-cycle has one node at depth 1 and one at depth 2, so the parity
+    classes are {seed, depth 2} and {depth 1}, and the smaller (odd) one is kept."""
+    import ctypes as C
+
+    from bsms_gnn_b200._lib import check, lib
+    fe = np.array([[0, 1, 2, 3, 4, 5], [1, 2, 0, 4, 5, 3]], dtype=np.int64)
+    labels = np.empty(6, dtype=np.int64)
+    nc = C.c_int64()
+    check(lib.bsms_components_host(fe.ctypes.data, 6, 6, labels.ctypes.data, C.byref(nc)))
+    assert nc.value == 2 and labels.tolist() == [0, 0, 0, 1, 1, 1]
+    pos = np.array([[0.0, 0.0], [1.0, 0.0], [0.4, 0.1], [5.0, 5.0], [6.0, 5.0], [5.4, 5.1]], dtype=np.float32)
+    k_n, e_n = hierarchy.bistride_level_numpy(fe, pos, 6)
+    k_c, e_c = hierarchy.bistride_level_native(fe, pos, 6)
+    gs, ids = hierarchy.build_hierarchy_native(fe, 1, 6, pos)
+    assert np.array_equal(k_n, k_c) and np.array_equal(e_n, e_c)
+    assert np.array_equal(ids[0], k_n) and np.array_equal(gs[1], e_n)
+    # seeds are the nodes nearest the cluster centroids (2 and 5); depth-1 nodes (their successors 0 and 3) are the
+    # smaller parity class of each cluster
+    assert k_n.tolist() == [0, 3]
