@@ -104,18 +104,34 @@ struct DetSegs {
   const float* part;
   int stride;
 };
-// dst[row, col] += sum over the CTAs' partial blocks (ascending) and their per-warp repetitions (ascending): one thread
-// per element, one fixed order
+// dst[row, col] += sum over the CTAs' partial blocks and their per-warp repetitions, in ONE fixed order: 64 elements per
+// CTA, eight interleaved chains per element (thread group j takes blocks j, j+8, ... into one accumulator and blocks
+// j+4, j+12, ... into a second one), combined in a fixed sequence — every run adds the same numbers in the same order
 __global__ void __launch_bounds__(256) k_det_reduce(const DetSegs a) {
+  __shared__ float s_part[4][64];
   const DetSeg sg = a.s[blockIdx.y];
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= sg.rows * sg.cols) return;
-  const int row = idx / sg.cols, col = idx - row * sg.cols;
-  const float* src = a.part + (size_t)sg.part0 * a.stride + sg.src_off + row * sg.src_cols + col;
-  float sum = 0.f;
-  for (int c = 0; c < sg.nparts; ++c)
-    for (int rep = 0; rep < sg.reps; ++rep) sum += src[(size_t)c * a.stride + (size_t)rep * sg.rows * sg.src_cols];
-  sg.dst[(size_t)row * sg.ldd + col] += sum;
+  const int e = threadIdx.x & 63, j = threadIdx.x >> 6;
+  const int idx = blockIdx.x * 64 + e;
+  const bool live = idx < sg.rows * sg.cols;
+  float acc0 = 0.f, acc1 = 0.f;
+  int row = 0, col = 0;
+  if (live) {
+    row = idx / sg.cols;
+    col = idx - row * sg.cols;
+    const float* src = a.part + (size_t)sg.part0 * a.stride + sg.src_off + row * sg.src_cols + col;
+    const size_t rep_stride = (size_t)sg.rows * sg.src_cols;
+    for (int c = j; c < sg.nparts; c += 8) {
+      const float* p0 = src + (size_t)c * a.stride;
+      for (int rep = 0; rep < sg.reps; ++rep) acc0 += p0[rep * rep_stride];
+      if (c + 4 < sg.nparts) {
+        const float* p1 = p0 + (size_t)4 * a.stride;
+        for (int rep = 0; rep < sg.reps; ++rep) acc1 += p1[rep * rep_stride];
+      }
+    }
+  }
+  s_part[j][e] = acc0 + acc1;
+  __syncthreads();
+  if (live && j == 0) sg.dst[(size_t)row * sg.ldd + col] += ((s_part[0][e] + s_part[1][e]) + s_part[2][e]) + s_part[3][e];
 }
 
 int det_reduce(const float* part, int stride, const DetSeg* segs, int nseg, cudaStream_t st) {
@@ -132,7 +148,7 @@ int det_reduce(const float* part, int stride, const DetSeg* segs, int nseg, cuda
   a.part = part;
   a.stride = stride;
   ProfScope ps_(PK_WGRAD, st);
-  k_det_reduce<<<dim3(ceil_div(most, 256), nseg), 256, 0, st>>>(a);
+  k_det_reduce<<<dim3(ceil_div(most, 64), nseg), 256, 0, st>>>(a);
   BSMS_LAUNCHED();
   return BSMS_OK;
 }
