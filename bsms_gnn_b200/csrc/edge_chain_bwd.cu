@@ -614,10 +614,8 @@ __global__ void __launch_bounds__(256, 1) k_edge_chain_bwd(const EdgeBwdParams p
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  if (DET || p.part) {
-    // per-CTA / per-warp partial sums, added up in a fixed order by det_reduce (layout: kDetEdgeBwdStride); also the
-    // non-deterministic path may choose it (BSMS_FLUSH=part): plain stores + one small reduction kernel instead of 148
-    // CTAs adding 192 KB each into the same addresses
+  if (DET) {
+    // per-CTA / per-warp partial sums, added up in a fixed order by det_reduce (layout: kDetEdgeBwdStride)
     float* part = p.part + (size_t)blockIdx.x * kDetEdgeBwdStride;
 #pragma unroll 1
     for (int l = 0; l < 3; ++l) {
@@ -735,7 +733,7 @@ int edge_chain_backward(const bsms_level_plan* pl, const bsms_gmp_weights* w, co
   const size_t smem = edge_chain_bwd_smem();
   // BSMS_BWD_F2=0 (development switch) turns the packed fp32x2 epilogue arithmetic off
   static const bool f2 = !(getenv("BSMS_BWD_F2") && atoi(getenv("BSMS_BWD_F2")) == 0);
-  if (g0_rows && !part) {
+  if ((g0_rows == nullptr) != (part == nullptr)) {
     set_error("edge_chain_backward: the deterministic variant needs both the row buffer and the partial-sum block");
     return BSMS_EINVAL;
   }

@@ -555,10 +555,9 @@ extern "C" size_t bsms_gmp_workspace_bytes(int32_t B, int32_t N, int32_t E, int3
   if (mode == BSMS_MODE_BF16 || (mode == BSMS_MODE_FP16X3 && !backward)) {
     // fused tensor-core path: no per-edge buffer at all — except under the deterministic option (bf16), which moves one
     // [B*E, 128] row tensor through HBM per direction and keeps one partial-sum block per CTA
-    const size_t det = (g_deterministic && mode == BSMS_MODE_BF16) ? f(Re * D) : 0;
+    const size_t det = (g_deterministic && mode == BSMS_MODE_BF16) ? f(Re * D) + (backward ? align_up(det_part_bytes(), 256) : 0) : 0;
     if (!backward) return node_bufs + scratch + det;
-    // + one partial-sum block per CTA (deterministic option, or BSMS_FLUSH=part)
-    return node_bufs + 4 * f(Rn * D) + 2 * f(Rn * 256) + scratch + det + (mode == BSMS_MODE_BF16 ? align_up(det_part_bytes(), 256) : 0);
+    return node_bufs + 4 * f(Rn * D) + 2 * f(Rn * 256) + scratch + det;
   }
   // fp32 path (and the fp32 backward the fp16x3 mode uses): per-edge activations are materialised
   size_t fwd = node_bufs + f(Re * D) + scratch;

@@ -1,9 +1,6 @@
 // GMP block on the tensor-core path (BSMS_MODE_BF16 / BSMS_MODE_FP16X3): orchestration of the fused
 // edge kernels (edge_chain*.cu) and the node-level tcgen05 GEMMs (node_gemm.cu).
 // Reference: src/ops/basic.py:48-98.
-#include <stdlib.h>
-#include <string.h>
-
 #include "chain.cuh"
 
 namespace bsms {
@@ -310,11 +307,10 @@ int gmp_backward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const 
   // deterministic option: edge rows (forward recompute / edge-input gradient) and the per-CTA partial-sum block
   float* det_rows = nullptr;
   float* det_part = nullptr;
-  // BSMS_FLUSH=part (experiment switch): the per-CTA gradient sums leave through the partial-sum block + one ordered
-  // reduction in the default (non-deterministic) path too, instead of red.add / atomicAdd flushes into shared addresses
-  static const bool flush_part = getenv("BSMS_FLUSH") && strcmp(getenv("BSMS_FLUSH"), "part") == 0;
-  if (det_enabled()) det_rows = ar.take<float>(std::max<long long>(Re, 1) * kD);
-  if (det_enabled() || flush_part) det_part = reinterpret_cast<float*>(ar.take<uint8_t>(det_part_bytes()));
+  if (det_enabled()) {
+    det_rows = ar.take<float>(std::max<long long>(Re, 1) * kD);
+    det_part = reinterpret_cast<float*>(ar.take<uint8_t>(det_part_bytes()));
+  }
   if (!ar.ok()) {
     set_error("bsms_gmp_backward: workspace too small for the tensor-core path");
     return BSMS_EWORKSPACE;
@@ -351,7 +347,7 @@ int gmp_backward_tc(const bsms_level_plan* pl, const bsms_gmp_weights* w, const 
       TC_TRY(launch_edge_grad_segsum(det_rows, pl, gPsPd, B, st));
     } else {
       BSMS_CUDA(cudaMemsetAsync(gPsPd, 0, (size_t)Rn * 256 * sizeof(float), st));
-      TC_TRY(edge_chain_backward(pl, w, gr, n.PsPd, pos, pos_batched, B, P, wpack, gcat, kD, gPsPd, st, true, nullptr, det_part));
+      TC_TRY(edge_chain_backward(pl, w, gr, n.PsPd, pos, pos_batched, B, P, wpack, gcat, kD, gPsPd, st, true));
     }
     WgradParams pr[2] = {wgrad_problem(gPsPd, 256, x, kD, gr->w_edge[0] + (P + 1), ldw1, nullptr, Rn),
                          wgrad_problem(gPsPd + 128, 256, x, kD, gr->w_edge[0] + (P + 1 + kD), ldw1, nullptr, Rn)};
